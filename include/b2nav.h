@@ -1,0 +1,198 @@
+/* b2nav.h - C ABI of libb2nav.so: the B200 (sm_100a) implementation of the two data-parallel hot
+ * loops of bostoncleek/ROS-Turtlebot-Navigation.
+ *
+ *   controller::MPPI::newControls()       reference: controller/src/controller/mppi.cpp:72-140
+ *   bmapping::ParticleFilter::SLAM()      reference: bmapping/src/bmapping/particle_filter.cpp:141-251
+ *
+ * The reference has no FFI: its boundary is two C++ class surfaces linked statically into ROS nodes
+ * (callers: nuturtle_robot/src/mppi_waypoints_node.cpp:186-199,216,257,265 and
+ * bmapping/src/turtle_mapping_node.cpp:392-410,474,479,494).  The drop-in C++ classes with the same
+ * names and signatures live in include/controller/mppi.hpp and include/bmapping/particle_filter.hpp
+ * and are thin pimpl wrappers over the functions below.  Each entry point cites the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types;
+ *   - every function returns B2N_OK (0) or a negative b2n_status; b2n_last_error() gives the text
+ *     of the most recent failure on the calling thread;
+ *   - handles own their device and host memory; in/out arrays are owned by the caller and only
+ *     borrowed for the duration of the call;
+ *   - handles are not thread-safe (the reference's callers are single-threaded spin loops);
+ *   - there is NO CPU fallback: without a usable CUDA device create() fails with B2N_ERR_CUDA.
+ */
+#ifndef B2NAV_H
+#define B2NAV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2n_status {
+  B2N_OK = 0,
+  B2N_ERR_INVALID_ARGUMENT = -1,   /* reference: std::invalid_argument / std::out_of_range */
+  B2N_ERR_CUDA = -2,               /* no device, launch or allocation failure */
+  B2N_ERR_OFF_MAP = -3,            /* reference: world2Grid/world2RowMajor throw, grid_mapper.cpp:817-825,854-862 */
+  B2N_ERR_UNSUPPORTED = -4,        /* size outside what the kernels are built for */
+  B2N_ERR_COMM = -5,               /* NCCL failure */
+  B2N_ERR_NUMERIC = -6             /* reference: "eta is 0", particle_filter.cpp:577-580 */
+} b2n_status;
+
+const char *b2n_last_error(void);
+/* number of CUDA devices visible to the library (0 when there is no usable driver) */
+int b2n_device_count(void);
+/* writes "libb2nav <version> sm_100a"; returns the number of bytes needed */
+int b2n_version(char *buf, size_t cap);
+
+/* ======================================================================================== MPPI */
+
+typedef struct b2n_mppi b2n_mppi;
+
+/* constructor arguments of controller::CartModel (mppi.hpp:33), controller::LossFunc (mppi.hpp:63)
+ * and controller::MPPI (mppi.hpp:133-141), plus where this handle sits in a sharded job */
+typedef struct b2n_mppi_params {
+  double wheel_radius, wheel_base;
+  double Q[3], R[2], P1[3];          /* diagonals */
+  double lambda, max_wheel_vel, ul_var, ur_var, horizon, dt;
+  int32_t rollouts;                  /* rollouts simulated by THIS handle */
+  int32_t rollout_offset;            /* global index of this handle's rollout 0 (0 when unsharded) */
+  int32_t rollouts_total;            /* K of the whole job (0 or == rollouts when unsharded) */
+  int32_t device;                    /* CUDA device ordinal, -1 = current device */
+} b2n_mppi_params;
+
+/* controller::MPPI::MPPI, mppi.cpp:28-51; steps = (int)(horizon/dt) exactly as mppi.cpp:47 */
+int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out);
+void b2n_mppi_destroy(b2n_mppi *h);
+int b2n_mppi_steps(const b2n_mppi *h);
+
+/* controller::MPPI::setInitialControls, mppi.cpp:54-61 */
+int b2n_mppi_set_initial_controls(b2n_mppi *h, double ul, double ur);
+/* controller::MPPI::setWaypoint, mppi.cpp:64-69 */
+int b2n_mppi_set_waypoint(b2n_mppi *h, double x, double y, double theta);
+/* controller::MPPI::newControls, mppi.cpp:72-140: synchronous; the controls are on the host at return */
+int b2n_mppi_new_controls(b2n_mppi *h, double x, double y, double theta, double *ul, double *ur);
+
+/* The same call split in two so that many steps can be queued without a host round trip:
+ * enqueue() launches the kernels for one newControls() on the handle's stream, wait() blocks until
+ * the most recently enqueued call is done and returns its controls. */
+int b2n_mppi_enqueue(b2n_mppi *h, double x, double y, double theta);
+int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur);
+
+/* Noise.  The reference draws from one process-global std::mt19937_64 (rigid2d/src/rigid2d/
+ * utilities.cpp:12-24); a serial engine cannot feed K*T lanes, so the kernels use a counter-based
+ * Philox4x32-10 stream keyed by (seed; call, rollout, step) - results do not depend on how the
+ * rollouts are sharded.  For runs that must consume the reference's own variates, pass them in. */
+int b2n_mppi_seed(b2n_mppi *h, uint64_t seed, uint32_t first_call);
+/* perturbations for the NEXT call only, du[k][t][0..1] = (duL, duR), k local to this handle */
+int b2n_mppi_set_noise(b2n_mppi *h, const double *du, size_t count);
+
+/* Test / bench taps (the reference keeps these as private Eigen members, mppi.hpp:169-183) */
+int b2n_mppi_set_capture(b2n_mppi *h, int on);                    /* keep J and du of each call */
+int b2n_mppi_get_states(b2n_mppi *h, float *out, size_t count);   /* [K][T][3] x,y,theta of the last call */
+int b2n_mppi_get_cost_to_go(b2n_mppi *h, double *out, size_t count);  /* [K][T], needs capture */
+int b2n_mppi_get_noise(b2n_mppi *h, double *out, size_t count);   /* [K][T][2], needs capture */
+int b2n_mppi_get_weights(b2n_mppi *h, double *out, size_t count); /* [K][T] normalised, needs capture */
+int b2n_mppi_get_plan(b2n_mppi *h, double *out, size_t count);    /* [2][T] the control plan u */
+int b2n_mppi_set_plan(b2n_mppi *h, const double *u, size_t count);
+/* [T][6] per-step (min J, sum e, sum e*duL, sum e*duR, sum duL, sum duR) of this handle's rollouts */
+int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count);
+
+/* Extension absent from the reference: running loss +=
+ * weight * max(0, d0 - dist(x,y))^2 with dist looked up as grid_mapper.cpp:852-898; off-map states
+ * pay off_map.  dist == NULL switches the term off. */
+int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int ysize, double xmin, double ymin,
+                                double resolution, double weight, double d0, double off_map);
+
+/* Launch on a caller-owned cudaStream_t (pass the pointer value); NULL restores the handle's own */
+int b2n_mppi_set_stream(b2n_mppi *h, void *cuda_stream);
+/* Write the K*T*3 state tensor round-robin into n buffers (n*K*T*12 bytes) so that back-to-back
+ * calls stream through HBM instead of re-dirtying the same L2 lines; n = 1 is the default */
+int b2n_mppi_set_state_ring(b2n_mppi *h, int n);
+/* kernels launched by this handle since creation, and average device time (ms) of the rollout
+ * kernel measured with CUDA events on the launching stream since the last call to this function */
+int b2n_mppi_launch_count(const b2n_mppi *h, uint64_t *launches);
+int b2n_mppi_set_kernel_timing(b2n_mppi *h, int on);
+int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples);
+
+/* Sharded operation: every rank simulates its slice of the rollouts, the [T][6]
+ * partials are exchanged with ONE ncclAllGather, every rank applies the identical update.
+ * unique_id is the 128-byte ncclUniqueId made by b2n_comm_unique_id() on one rank and distributed
+ * by the caller (e.g. a torch.distributed broadcast). */
+int b2n_comm_unique_id(void *out128);
+int b2n_mppi_comm_init(b2n_mppi *h, int rank, int nranks, const void *unique_id128);
+
+/* ======================================================================================== RBPF */
+
+typedef struct b2n_pf b2n_pf;
+
+/* bmapping::LaserProperties (sensor_model.hpp:63-76), bmapping::GridMapper ctor (grid_mapper.hpp:121-122,
+ * square maps as the reference assumes, grid_mapper.cpp:352-353) and bmapping::ParticleFilter ctor
+ * (particle_filter.hpp:112-130).  Trs (robot->sensor) is the identity, as in turtle_mapping_node.cpp:397. */
+typedef struct b2n_pf_params {
+  /* lidar */
+  float beam_min, beam_max, beam_delta, range_min, range_max;
+  double z_hit, z_short, z_max, z_rand, sigma_hit;
+  /* map */
+  double resolution, xmin, xmax, ymin, ymax;
+  /* filter */
+  int32_t num_particles;             /* particles held by THIS handle */
+  int32_t k;                         /* mode samples of the improved proposal */
+  double srr, srt, str, stt;
+  double motion_noise_theta, motion_noise_x, motion_noise_y;
+  double sample_range_theta, sample_range_x, sample_range_y;
+  double scan_likelihood_min, scan_likelihood_max, pose_likelihood_min, pose_likelihood_max;
+  double init_pose[3];               /* theta, x, y  (particle_filter.cpp:133) */
+  int32_t particle_offset;           /* global index of this handle's particle 0 */
+  int32_t particles_total;           /* N of the whole job (0 or == num_particles when unsharded) */
+  int32_t device;
+  int32_t max_beams;                 /* capacity for scan length; 0 -> 1024 */
+} b2n_pf_params;
+
+int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out);
+void b2n_pf_destroy(b2n_pf *h);
+
+/* bmapping::ParticleFilter::SLAM, particle_filter.cpp:141-251.
+ * twist = (w, vx, vy) body twist of the scan interval, odometry poses = (theta, x, y).
+ * The scan matcher (PCL ICP, cloud_alignment.cpp:37-72) stays on the caller's side of the boundary:
+ * icp_ok == 0 selects the motion-model branch (particle_filter.cpp:161-176), icp_ok != 0 the
+ * improved-proposal branch (:178-233) with icp_pose = (theta, x, y) of Ticp.
+ * Returns B2N_ERR_OFF_MAP where the reference would throw because an end point left the map. */
+int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3], const double cur_odom[3],
+                const double prev_odom[3], int icp_ok, const double icp_pose[3]);
+/* bmapping::ParticleFilter::getRobotState, particle_filter.cpp:255-274 -> (theta, x, y) */
+int b2n_pf_get_robot_state(b2n_pf *h, double pose[3]);
+/* bmapping::ParticleFilter::newMap, particle_filter.cpp:277-291 + grid_mapper.cpp:185-226 */
+int b2n_pf_new_map(b2n_pf *h, int8_t *out, size_t count);
+
+int b2n_pf_seed(b2n_pf *h, uint64_t seed, uint32_t first_call);
+/* standard normals for the NEXT call only: z[n][3] motion draws per particle (theta, x, y order),
+ * then one more value for the resampling draw: count = 3*N + 1 */
+int b2n_pf_set_noise(b2n_pf *h, const double *z, size_t count);
+
+/* Taps */
+int b2n_pf_grid_size(const b2n_pf *h, int *xsize, int *ysize);
+int b2n_pf_get_weights(b2n_pf *h, double *out, size_t count);
+int b2n_pf_set_weights(b2n_pf *h, const double *w, size_t count);
+int b2n_pf_get_poses(b2n_pf *h, double *poses, double *prev_poses, size_t count);   /* [N][3] theta,x,y */
+int b2n_pf_set_poses(b2n_pf *h, const double *poses, size_t count);
+/* outcome of the last SLAM(): N_eff as the reference prints it, whether it resampled, and the
+ * ancestor of every slot (identity when it did not) */
+int b2n_pf_get_resample(b2n_pf *h, int *neff, int *resampled, int32_t *ancestors, size_t count);
+/* one particle's map: log-odds (fp64), distance to nearest occupied cell (fp32), class (-1/0/1) */
+int b2n_pf_get_grid(b2n_pf *h, int particle, double *log_odds, float *occ_dist, int8_t *state, size_t count);
+int b2n_pf_set_grid(b2n_pf *h, int particle, const double *log_odds, const float *occ_dist, const int8_t *state,
+                    const int32_t *occ_order, int n_occ, size_t count);
+/* iteration order of the occupied-cell set (seeds of the distance transform), returns the count */
+int b2n_pf_get_occ_order(b2n_pf *h, int particle, int32_t *keys, size_t cap, int *n_occ);
+/* run only parts of SLAM(), for parity tests and kernel timing */
+int b2n_pf_likelihoods(b2n_pf *h, const float *scan, int n_beams, double *out, size_t count);
+int b2n_pf_set_stream(b2n_pf *h, void *cuda_stream);
+int b2n_pf_launch_count(const b2n_pf *h, uint64_t *launches);
+int b2n_pf_comm_init(b2n_pf *h, int rank, int nranks, const void *unique_id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2NAV_H */

@@ -1,0 +1,524 @@
+// mppi_api.cu - extern "C" MPPI entry points of libb2nav (see include/b2nav.h).
+// Host side of controller::MPPI (reference: controller/src/controller/mppi.cpp:28-69,72-140).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <nccl.h>
+
+#include "mppi_kernels.cuh"
+
+using namespace b2n;
+
+struct b2n_mppi
+{
+  b2n_mppi_params p;
+  int T = 0, K = 0, S = 1, device = 0;
+  int n_sm = 0, grid = 0;
+  size_t smem = 0;
+  bool tma_store = false;
+
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+
+  double xd[3] = {0, 0, 0}, uinit[2] = {0, 0};
+  uint64_t seed = 0;
+  uint32_t call = 0;
+
+  double *d_u[2] = {nullptr, nullptr};   // ping-pong plan [2][T]
+  int cur = 0;
+  float *d_states = nullptr;             // [ring][K][T][3]
+  int ring = 1, ring_pos = 0, last_slot = 0;
+  double *d_partials = nullptr;          // [grid][T][6]
+  double *d_merged = nullptr;            // [T][6]
+  double *d_gathered = nullptr;          // [nranks][T][6]
+  double *d_out = nullptr;               // [2]
+  double *d_stepstats = nullptr;         // [T][2]
+  double *h_out = nullptr;               // pinned [2]
+  double *d_ext = nullptr;               // [K][T][2]
+  bool ext_armed = false;
+  int capture = 0;
+  double *d_J = nullptr, *d_du = nullptr, *d_w = nullptr;
+
+  // obstacle field
+  float *d_obs = nullptr;
+  int obs_on = 0, obs_xsize = 0, obs_ysize = 0;
+  double obs_xmin = 0, obs_ymin = 0, obs_res = 1, obs_weight = 0, obs_d0 = 0, obs_off = 0;
+
+  // sharding
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  // accounting
+  uint64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;           // start/stop pairs
+  size_t ev_used = 0;
+  bool pending = false;
+};
+
+namespace
+{
+
+template <int S>
+int launch_rollout_s(b2n_mppi *h, const MppiArgs &a)
+{
+  mppi_rollout_kernel<S><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);
+  return 0;
+}
+
+size_t rollout_smem(int S) { return (size_t)kMppiWarps * 2 * 32 * S * 3 * sizeof(float) + (size_t)32 * S * 6 * sizeof(double); }
+
+template <int S>
+cudaError_t configure_s(b2n_mppi *h)
+{
+  h->smem = rollout_smem(S);
+  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S>, kMppiThreads, h->smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const int want = (h->K + kMppiWarps - 1) / kMppiWarps;
+  h->grid = std::max(1, std::min(want, per_sm * h->n_sm));
+  return cudaSuccess;
+}
+
+int set_device(const b2n_mppi *h)
+{
+  B2N_CUDA(cudaSetDevice(h->device));
+  return B2N_OK;
+}
+
+int enqueue_call(b2n_mppi *h, double x, double y, double theta)
+{
+  const b2n_mppi_params &p = h->p;
+  MppiArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.r_half = p.wheel_radius / 2.0;
+  a.r_over_L = p.wheel_radius / p.wheel_base;
+  for (int i = 0; i < 3; i++) { a.Q[i] = p.Q[i]; a.P1[i] = p.P1[i]; a.xd[i] = h->xd[i]; }
+  a.R[0] = p.R[0]; a.R[1] = p.R[1];
+  a.inv_lambda = 1.0 / p.lambda;
+  a.h = p.dt;
+  a.h_sixth = p.dt / 6.0;
+  a.sigL = std::sqrt(p.ul_var);       // mppi.cpp:176-177
+  a.sigR = std::sqrt(p.ur_var);
+  a.x0[0] = x; a.x0[1] = y; a.x0[2] = theta;   // mppi.cpp:75-76
+  a.T = h->T; a.K = h->K; a.k_offset = p.rollout_offset;
+  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.call = h->call;
+  a.external_noise = h->ext_armed ? 1 : 0;
+  a.capture = h->capture;
+  a.tma_store = h->tma_store ? 1 : 0;
+  a.obs_on = h->obs_on; a.obs_xsize = h->obs_xsize; a.obs_ysize = h->obs_ysize;
+  a.obs_xmin = h->obs_xmin; a.obs_ymin = h->obs_ymin; a.obs_res = h->obs_res;
+  a.obs_xmax = h->obs_xmin + h->obs_xsize * h->obs_res;
+  a.obs_ymax = h->obs_ymin + h->obs_ysize * h->obs_res;
+  a.obs_weight = h->obs_weight; a.obs_d0 = h->obs_d0; a.obs_off = h->obs_off; a.obs_dist = h->d_obs;
+  a.u_plan = h->d_u[h->cur];
+  h->last_slot = h->ring_pos;
+  a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
+  h->ring_pos = (h->ring_pos + 1) % h->ring;
+  a.ext = h->d_ext; a.J_out = h->d_J; a.du_out = h->d_du; a.partials = h->d_partials;
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing && h->ev_used + 2 <= h->ev.size()) {
+    e0 = h->ev[h->ev_used]; e1 = h->ev[h->ev_used + 1];
+    h->ev_used += 2;
+    B2N_CUDA(cudaEventRecord(e0, h->stream));
+  }
+  switch (h->S) {
+    case 1: launch_rollout_s<1>(h, a); break;
+    case 2: launch_rollout_s<2>(h, a); break;
+    case 4: launch_rollout_s<4>(h, a); break;
+    default: launch_rollout_s<8>(h, a); break;
+  }
+  B2N_CUDA(cudaGetLastError());
+  if (e1) B2N_CUDA(cudaEventRecord(e1, h->stream));
+  h->launches++;
+
+  MppiUpdateArgs u;
+  std::memset(&u, 0, sizeof(u));
+  u.T = h->T;
+  u.inv_lambda = a.inv_lambda;
+  u.k_total = (double)(p.rollouts_total > 0 ? p.rollouts_total : p.rollouts);
+  u.umax = p.max_wheel_vel;
+  u.uinit[0] = h->uinit[0]; u.uinit[1] = h->uinit[1];
+  u.u_cur = h->d_u[h->cur];
+  u.u_next = h->d_u[h->cur ^ 1];
+  u.out = h->d_out;
+  u.stepstats = h->d_stepstats;
+  u.merged = h->d_merged;
+  if (h->nranks > 1) {
+    // local merge -> one allgather of [T][6] doubles -> identical update on every rank
+    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 1;
+    mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+    B2N_CUDA(cudaGetLastError());
+    h->launches++;
+    ncclResult_t r = ncclAllGather(h->d_merged, h->d_gathered, (size_t)h->T * 6, ncclDouble, h->comm, h->stream);
+    B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
+    u.partials = h->d_gathered; u.n_partials = h->nranks; u.merge_only = 0;
+  } else {
+    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
+  }
+  mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  B2N_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+
+  h->cur ^= 1;
+  h->call++;
+  h->ext_armed = false;
+  h->pending = true;
+  return B2N_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
+{
+  B2N_REQUIRE(params && out, B2N_ERR_INVALID_ARGUMENT, "b2n_mppi_create: null argument");
+  *out = nullptr;
+  const b2n_mppi_params &p = *params;
+  B2N_REQUIRE(p.rollouts > 0, B2N_ERR_INVALID_ARGUMENT, "rollouts must be positive (got %d)", p.rollouts);
+  B2N_REQUIRE(p.dt > 0.0 && p.horizon > 0.0, B2N_ERR_INVALID_ARGUMENT, "horizon and dt must be positive");
+  B2N_REQUIRE(p.lambda > 0.0, B2N_ERR_INVALID_ARGUMENT, "lambda must be positive");
+  B2N_REQUIRE(p.wheel_base != 0.0, B2N_ERR_INVALID_ARGUMENT, "wheel_base must be non-zero");
+  B2N_REQUIRE(p.ul_var >= 0.0 && p.ur_var >= 0.0, B2N_ERR_INVALID_ARGUMENT, "control variances must be non-negative");
+  const int T = static_cast<int>(p.horizon / p.dt);   // mppi.cpp:47, truncation included
+  B2N_REQUIRE(T >= 1, B2N_ERR_INVALID_ARGUMENT, "horizon/dt gives %d steps", T);
+  B2N_REQUIRE(T <= 32 * kMppiMaxS, B2N_ERR_UNSUPPORTED, "steps = %d exceeds the %d the rollout kernel is built for", T,
+              32 * kMppiMaxS);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("b2n_mppi_create: no CUDA device (libb2nav has no CPU path)");
+    return B2N_ERR_CUDA;
+  }
+  b2n_mppi *h = new (std::nothrow) b2n_mppi();
+  B2N_REQUIRE(h, B2N_ERR_CUDA, "out of host memory");
+  h->p = p;
+  h->T = T;
+  h->K = p.rollouts;
+  int S = (T + 31) / 32;
+  h->S = S <= 1 ? 1 : S <= 2 ? 2 : S <= 4 ? 4 : 8;
+  if (p.device >= 0) h->device = p.device; else cudaGetDevice(&h->device);
+
+#define B2N_TRY(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);         \
+      b2n_mppi_destroy(h);                                                                     \
+      return B2N_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+  B2N_TRY(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  B2N_TRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libb2nav is built for sm_100a only", h->device, prop.major, prop.minor);
+    b2n_mppi_destroy(h);
+    return B2N_ERR_CUDA;
+  }
+  h->n_sm = prop.multiProcessorCount;
+  B2N_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  switch (h->S) {
+    case 1: B2N_TRY(configure_s<1>(h)); break;
+    case 2: B2N_TRY(configure_s<2>(h)); break;
+    case 4: B2N_TRY(configure_s<4>(h)); break;
+    default: B2N_TRY(configure_s<8>(h)); break;
+  }
+  h->tma_store = ((size_t)T * 3 * sizeof(float)) % 16 == 0;   // cp.async.bulk moves 16-byte granules
+
+  const size_t KT = (size_t)h->K * T;
+  B2N_TRY(cudaMalloc(&h->d_u[0], 2 * T * sizeof(double)));
+  B2N_TRY(cudaMalloc(&h->d_u[1], 2 * T * sizeof(double)));
+  B2N_TRY(cudaMemsetAsync(h->d_u[0], 0, 2 * T * sizeof(double), h->stream));   // mppi.cpp:157-170
+  B2N_TRY(cudaMemsetAsync(h->d_u[1], 0, 2 * T * sizeof(double), h->stream));
+  B2N_TRY(cudaMalloc(&h->d_states, KT * 3 * sizeof(float)));
+  B2N_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * T * 6 * sizeof(double)));
+  B2N_TRY(cudaMalloc(&h->d_merged, (size_t)T * 6 * sizeof(double)));
+  B2N_TRY(cudaMalloc(&h->d_out, 2 * sizeof(double)));
+  B2N_TRY(cudaMalloc(&h->d_stepstats, (size_t)T * 2 * sizeof(double)));
+  B2N_TRY(cudaMallocHost(&h->h_out, 2 * sizeof(double)));
+  B2N_TRY(cudaStreamSynchronize(h->stream));
+#undef B2N_TRY
+  *out = h;
+  return B2N_OK;
+}
+
+void b2n_mppi_destroy(b2n_mppi *h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) ncclCommDestroy(h->comm);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  cudaFree(h->d_u[0]); cudaFree(h->d_u[1]); cudaFree(h->d_states); cudaFree(h->d_partials);
+  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_stepstats);
+  cudaFree(h->d_ext); cudaFree(h->d_J); cudaFree(h->d_du); cudaFree(h->d_w); cudaFree(h->d_obs);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  cudaGetLastError();
+  delete h;
+}
+
+int b2n_mppi_steps(const b2n_mppi *h) { return h ? h->T : B2N_ERR_INVALID_ARGUMENT; }
+
+int b2n_mppi_set_initial_controls(b2n_mppi *h, double ul, double ur)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (int rc = set_device(h)) return rc;
+  h->uinit[0] = ul; h->uinit[1] = ur;
+  std::vector<double> u(2 * h->T);
+  for (int t = 0; t < h->T; t++) { u[t] = ul; u[h->T + t] = ur; }
+  B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  return B2N_OK;
+}
+
+int b2n_mppi_set_waypoint(b2n_mppi *h, double x, double y, double theta)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  h->xd[0] = x; h->xd[1] = y; h->xd[2] = theta;
+  return B2N_OK;
+}
+
+int b2n_mppi_enqueue(b2n_mppi *h, double x, double y, double theta)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (int rc = set_device(h)) return rc;
+  return enqueue_call(h, x, y, theta);
+}
+
+int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  B2N_REQUIRE(h->pending, B2N_ERR_INVALID_ARGUMENT, "b2n_mppi_wait: nothing enqueued");
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  if (ul) *ul = h->h_out[0];
+  if (ur) *ur = h->h_out[1];
+  return B2N_OK;
+}
+
+int b2n_mppi_new_controls(b2n_mppi *h, double x, double y, double theta, double *ul, double *ur)
+{
+  B2N_REQUIRE(h && ul && ur, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = b2n_mppi_enqueue(h, x, y, theta)) return rc;
+  return b2n_mppi_wait(h, ul, ur);
+}
+
+int b2n_mppi_seed(b2n_mppi *h, uint64_t seed, uint32_t first_call)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  h->seed = seed; h->call = first_call;
+  return B2N_OK;
+}
+
+int b2n_mppi_set_noise(b2n_mppi *h, const double *du, size_t count)
+{
+  B2N_REQUIRE(h && du, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t need = (size_t)h->K * h->T * 2;
+  B2N_REQUIRE(count == need, B2N_ERR_INVALID_ARGUMENT, "noise count %zu, expected K*T*2 = %zu", count, need);
+  if (int rc = set_device(h)) return rc;
+  if (!h->d_ext) B2N_CUDA(cudaMalloc(&h->d_ext, need * sizeof(double)));
+  B2N_CUDA(cudaMemcpyAsync(h->d_ext, du, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  h->ext_armed = true;
+  return B2N_OK;
+}
+
+int b2n_mppi_set_capture(b2n_mppi *h, int on)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (int rc = set_device(h)) return rc;
+  const size_t KT = (size_t)h->K * h->T;
+  if (on && !h->d_J) {
+    B2N_CUDA(cudaMalloc(&h->d_J, KT * sizeof(double)));
+    B2N_CUDA(cudaMalloc(&h->d_du, KT * 2 * sizeof(double)));
+    B2N_CUDA(cudaMalloc(&h->d_w, KT * sizeof(double)));
+  }
+  h->capture = on ? 1 : 0;
+  return B2N_OK;
+}
+
+static int copy_out(b2n_mppi *h, void *dst, const void *src, size_t bytes)
+{
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  B2N_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return B2N_OK;
+}
+
+int b2n_mppi_get_states(b2n_mppi *h, float *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t need = (size_t)h->K * h->T * 3;
+  B2N_REQUIRE(count == need, B2N_ERR_INVALID_ARGUMENT, "states count %zu, expected K*T*3 = %zu", count, need);
+  return copy_out(h, out, h->d_states + (size_t)h->last_slot * need, need * sizeof(float));
+}
+
+int b2n_mppi_get_cost_to_go(b2n_mppi *h, double *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->capture && h->d_J, B2N_ERR_INVALID_ARGUMENT, "cost-to-go needs b2n_mppi_set_capture(h, 1) before the call");
+  const size_t need = (size_t)h->K * h->T;
+  B2N_REQUIRE(count == need, B2N_ERR_INVALID_ARGUMENT, "count %zu, expected K*T = %zu", count, need);
+  return copy_out(h, out, h->d_J, need * sizeof(double));
+}
+
+int b2n_mppi_get_noise(b2n_mppi *h, double *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->capture && h->d_du, B2N_ERR_INVALID_ARGUMENT, "noise needs b2n_mppi_set_capture(h, 1) before the call");
+  const size_t need = (size_t)h->K * h->T * 2;
+  B2N_REQUIRE(count == need, B2N_ERR_INVALID_ARGUMENT, "count %zu, expected K*T*2 = %zu", count, need);
+  return copy_out(h, out, h->d_du, need * sizeof(double));
+}
+
+int b2n_mppi_get_weights(b2n_mppi *h, double *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->capture && h->d_J, B2N_ERR_INVALID_ARGUMENT, "weights need b2n_mppi_set_capture(h, 1) before the call");
+  const size_t need = (size_t)h->K * h->T;
+  B2N_REQUIRE(count == need, B2N_ERR_INVALID_ARGUMENT, "count %zu, expected K*T = %zu", count, need);
+  if (int rc = set_device(h)) return rc;
+  const int threads = 256;
+  mppi_weights_kernel<<<(unsigned)((need + threads - 1) / threads), threads, 0, h->stream>>>(h->d_J, h->d_stepstats, h->d_w, h->K,
+                                                                                            h->T, 1.0 / h->p.lambda);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  return copy_out(h, out, h->d_w, need * sizeof(double));
+}
+
+int b2n_mppi_get_plan(b2n_mppi *h, double *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(count == (size_t)2 * h->T, B2N_ERR_INVALID_ARGUMENT, "plan count %zu, expected 2*T = %d", count, 2 * h->T);
+  return copy_out(h, out, h->d_u[h->cur], count * sizeof(double));
+}
+
+int b2n_mppi_set_plan(b2n_mppi *h, const double *u, size_t count)
+{
+  B2N_REQUIRE(h && u, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(count == (size_t)2 * h->T, B2N_ERR_INVALID_ARGUMENT, "plan count %zu, expected 2*T = %d", count, 2 * h->T);
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  return B2N_OK;
+}
+
+int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count)
+{
+  B2N_REQUIRE(h && out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(count == (size_t)6 * h->T, B2N_ERR_INVALID_ARGUMENT, "partials count %zu, expected 6*T = %d", count, 6 * h->T);
+  if (int rc = set_device(h)) return rc;
+  MppiUpdateArgs u;
+  std::memset(&u, 0, sizeof(u));
+  u.T = h->T; u.inv_lambda = 1.0 / h->p.lambda; u.partials = h->d_partials; u.n_partials = h->grid;
+  u.merge_only = 1; u.merged = h->d_merged;
+  mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  return copy_out(h, out, h->d_merged, count * sizeof(double));
+}
+
+int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int ysize, double xmin, double ymin,
+                                double resolution, double weight, double d0, double off_map)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (int rc = set_device(h)) return rc;
+  if (!dist) { h->obs_on = 0; return B2N_OK; }
+  B2N_REQUIRE(xsize > 0 && ysize > 0 && resolution > 0.0, B2N_ERR_INVALID_ARGUMENT, "bad obstacle field geometry");
+  cudaFree(h->d_obs); h->d_obs = nullptr;
+  const size_t n = (size_t)xsize * ysize;
+  B2N_CUDA(cudaMalloc(&h->d_obs, n * sizeof(float)));
+  B2N_CUDA(cudaMemcpyAsync(h->d_obs, dist, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  h->obs_on = 1; h->obs_xsize = xsize; h->obs_ysize = ysize; h->obs_xmin = xmin; h->obs_ymin = ymin;
+  h->obs_res = resolution; h->obs_weight = weight; h->obs_d0 = d0; h->obs_off = off_map;
+  return B2N_OK;
+}
+
+int b2n_mppi_set_stream(b2n_mppi *h, void *cuda_stream)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return B2N_OK;
+}
+
+int b2n_mppi_set_state_ring(b2n_mppi *h, int n)
+{
+  B2N_REQUIRE(h && n >= 1, B2N_ERR_INVALID_ARGUMENT, "ring size must be >= 1");
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  float *fresh = nullptr;
+  B2N_CUDA(cudaMalloc(&fresh, (size_t)n * h->K * h->T * 3 * sizeof(float)));
+  cudaFree(h->d_states);
+  h->d_states = fresh; h->ring = n; h->ring_pos = 0; h->last_slot = 0;
+  return B2N_OK;
+}
+
+int b2n_mppi_launch_count(const b2n_mppi *h, uint64_t *launches)
+{
+  B2N_REQUIRE(h && launches, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  *launches = h->launches;
+  return B2N_OK;
+}
+
+int b2n_mppi_set_kernel_timing(b2n_mppi *h, int on)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (int rc = set_device(h)) return rc;
+  if (on && h->ev.empty()) {
+    h->ev.resize(2 * 4096);
+    for (auto &e : h->ev) B2N_CUDA(cudaEventCreate(&e));
+  }
+  h->timing = on != 0;
+  h->ev_used = 0;
+  return B2N_OK;
+}
+
+int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples)
+{
+  B2N_REQUIRE(h && avg_ms && samples, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  double total = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    B2N_CUDA(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    total += ms; n++;
+  }
+  *avg_ms = n ? total / n : 0.0;
+  *samples = n;
+  h->ev_used = 0;
+  return B2N_OK;
+}
+
+int b2n_mppi_comm_init(b2n_mppi *h, int rank, int nranks, const void *unique_id128)
+{
+  B2N_REQUIRE(h && unique_id128, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, B2N_ERR_INVALID_ARGUMENT, "bad rank %d of %d", rank, nranks);
+  if (int rc = set_device(h)) return rc;
+  ncclUniqueId id;
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(&id, unique_id128, sizeof(id));
+  ncclResult_t r = ncclCommInitRank(&h->comm, nranks, id, rank);
+  B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  h->rank = rank; h->nranks = nranks;
+  cudaFree(h->d_gathered); h->d_gathered = nullptr;
+  B2N_CUDA(cudaMalloc(&h->d_gathered, (size_t)nranks * h->T * 6 * sizeof(double)));
+  return B2N_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,276 @@
+"""GPU parity tests for the MPPI path, all through the C ABI of libb2nav.so (ctypes).
+
+Tolerances (BASELINE.json north_star): 1e-5 relative on trajectory states, weights and chosen
+controls.  The fp64 kernels land orders of magnitude inside that; the asserts below use the
+contract tolerance for the headline quantities and tighter ones where a regression would hide.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-5
+
+
+def _params(g):
+    return {k[2:]: (tuple(g[k]) if g[k].ndim else float(g[k])) for k in g.files if k.startswith("p_")}
+
+
+def make_gpu(pkg, horizon, dt, K, prm=orc.SHIPPED, **kw):
+    return pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
+                    prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], horizon, dt, K, **kw)
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)) if a.size else 0.0
+
+
+def check_call(gpu, o, ctrl_gpu, ctrl_o, states=True):
+    """Compare everything one newControls() produced on the GPU with the oracle's."""
+    g = o.get()
+    K, T = o.K, o.T
+    assert rel_err(ctrl_gpu, ctrl_o, 1e-3) < RTOL
+    assert rel_err(gpu.plan(), g["plan"], 1e-3) < RTOL
+    J = gpu.costToGo()                                  # [K][T]
+    assert rel_err(J, g["J"].T, 1e-6) < 1e-11          # what the 1e-5 on weights needs at lambda = 0.01
+    w = gpu.weights()
+    wo = g["w"].T
+    assert rel_err(w, wo, 1e-300) < RTOL
+    assert np.allclose(w.sum(axis=0), 1.0, rtol=1e-12, atol=0)
+    if states:
+        s = gpu.states()                                # fp32 tensor
+        so = g["states"]
+        assert np.max(np.abs(s - so) / np.maximum(np.abs(so), 1e-2)) < RTOL
+        assert np.array_equal(s, so.astype(np.float32)) or np.max(np.abs(s - so.astype(np.float32))) <= 2.4e-7 * np.max(np.abs(so))
+
+
+@pytest.mark.parametrize("name", ["mppi_c1_shipped_ref.npz", "mppi_c1_mild_ref.npz", "mppi_t64_shipped_ref.npz",
+                                  "mppi_t100_shipped_ref.npz"])
+def test_reference_fixture_with_reference_variates(gpu_pkg, name):
+    """The reference's own mt19937_64 variates (recorded from oracle/_ref) go in; its controls, plan and
+    min-subtracted cost-to-go must come out, call after call with the plan carried on the device."""
+    g = np.load(os.path.join(GOLD, name))
+    K, T = int(g["K"]), int(g["T"])
+    gpu = make_gpu(gpu_pkg, float(g["horizon"]), float(g["dt"]), K, _params(g))
+    assert gpu.steps == T
+    gpu.setCapture(True)
+    gpu.setInitialControls(0.0, 0.0)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=g["wpt"][2], x=g["wpt"][0], y=g["wpt"][1]))
+    for c in range(g["poses"].shape[0]):
+        gpu.setNoise(g["du"][c])
+        x, y, th = g["poses"][c]
+        v = gpu.newControls(gpu_pkg.Pose(theta=th, x=x, y=y))
+        assert rel_err([v.ul, v.ur], g["controls"][c], 1e-3) < RTOL, (c, v, g["controls"][c])
+        assert rel_err(gpu.plan(), g["plans"][c], 1e-3) < RTOL
+        J = gpu.costToGo().T
+        Jsub = J - J.min(axis=1, keepdims=True)
+        assert np.max(np.abs(Jsub - g["Jsub"][c])) < 1e-11 * np.max(J)
+        assert np.array_equal(gpu.noise(), g["du"][c])
+
+
+@pytest.mark.parametrize("hor,dt,K,prm", [
+    (0.5, 0.02, 128, orc.SHIPPED),      # config C1 (T = 25: generic store path, one step per lane)
+    (0.64, 0.01, 1000, orc.SHIPPED),    # T = 64, K not a multiple of the warps per CTA
+    (1.0, 0.01, 77, orc.SHIPPED),       # shipped horizon, T = 100: four steps per lane, last lanes idle
+    (1.28, 0.01, 256, orc.MILD),        # T = 128
+    (2.56, 0.01, 40, orc.MILD),         # T = 256: eight steps per lane
+    (0.01, 0.01, 5, orc.SHIPPED),       # T = 1: terminal loss only
+    (0.32, 0.01, 1, orc.SHIPPED),       # K = 1: weight is 1, update is the perturbation itself
+])
+def test_philox_closed_loop_matches_oracle(gpu_pkg, hor, dt, K, prm):
+    o = orc.OracleMppi(hor, dt, K, **prm)
+    gpu = make_gpu(gpu_pkg, hor, dt, K, prm)
+    assert gpu.steps == o.T
+    gpu.setCapture(True)
+    gpu.seed(42)
+    o.noise_philox(42)
+    for m in (gpu, o):
+        m.setInitialControls(0.2, 0.1)
+    o.setWaypoint(1.0, 0.0, 1.5707)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=1.5707, x=1.0, y=0.0))
+    pose = (0.0, 0.0, 0.0)
+    for c in range(8):
+        v = gpu.newControls(gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        co = o.newControls(*pose)
+        assert np.max(np.abs(gpu.noise() - o.get()["du"])) < 1e-13      # same Philox stream, libm-level differences
+        check_call(gpu, o, (v.ul, v.ur), co)
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
+
+
+def test_config_c1_hundred_calls(gpu_pkg):
+    """>= 100 consecutive newControls with the receding-horizon state carried, every call compared."""
+    hor, dt, K = 0.5, 0.02, 128
+    o = orc.OracleMppi(hor, dt, K)
+    gpu = make_gpu(gpu_pkg, hor, dt, K)
+    gpu.seed(7)
+    o.noise_philox(7)
+    o.setWaypoint(1.0, 0.0, 1.5707)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=1.5707, x=1.0, y=0.0))
+    pose = (0.0, 0.0, 0.0)
+    worst = 0.0
+    for c in range(100):
+        v = gpu.newControls(gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        co = o.newControls(*pose)
+        worst = max(worst, rel_err([v.ul, v.ur], co, 1e-3))
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
+    assert worst < RTOL
+    assert rel_err(gpu.plan(), o.get()["plan"], 1e-3) < RTOL
+
+
+def test_config_c2_full_size(gpu_pkg):
+    """BASELINE config 2: K = 16384, T = 64, shipped cost, against the oracle at full size."""
+    hor, dt, K = 0.64, 0.01, 16384
+    o = orc.OracleMppi(hor, dt, K)
+    gpu = make_gpu(gpu_pkg, hor, dt, K)
+    gpu.setCapture(True)
+    gpu.seed(42)
+    o.noise_philox(42)
+    o.setWaypoint(1.0, 0.0, 1.5707)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=1.5707, x=1.0, y=0.0))
+    pose = (0.0, 0.0, 0.0)
+    for c in range(3):
+        v = gpu.newControls(gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        co = o.newControls(*pose)
+        check_call(gpu, o, (v.ul, v.ur), co)
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
+
+
+def test_config_c4_shard_size_with_obstacles(gpu_pkg):
+    """BASELINE config 4 per-GPU shard (8192 of 65536 rollouts, T = 128) with the obstacle term on."""
+    hor, dt, K = 1.28, 0.01, 8192
+    xs = np.arange(200)
+    dist = np.hypot((xs[:, None] - 110) * 0.05, (xs[None, :] - 104) * 0.05).astype(np.float32)   # one obstacle cell
+    o = orc.OracleMppi(hor, dt, K)
+    gpu = make_gpu(gpu_pkg, hor, dt, K, rollout_offset=3 * 8192, rollouts_total=65536)
+    o.set_shard(3 * 8192)
+    o.set_obstacles(dist, -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+    gpu.setObstacleField(dist, -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+    gpu.setCapture(True)
+    gpu.seed(42)
+    o.noise_philox(42)
+    o.setWaypoint(1.0, 0.0, 0.0)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.0))
+    gpu.newControls(gpu_pkg.Pose(theta=0.0, x=0.3, y=0.1))
+    o.newControls(0.3, 0.1, 0.0)
+    g = o.get()
+    assert rel_err(gpu.costToGo(), g["J"].T, 1e-6) < 1e-11
+    assert np.max(np.abs(gpu.states() - g["states"])) < 1e-6
+    # the shard's control differs from the oracle's (the +1e-8 floor is normalised by the JOB's K),
+    # so compare the per-step partial sums instead: min J, sum e, sum e*du
+    p = gpu.partials()
+    Jo = g["J"]
+    m = Jo.min(axis=1)
+    e = np.exp(-(Jo - m[:, None]) / 0.01)
+    assert rel_err(p[:, 0], m, 1e-6) < 1e-11
+    assert rel_err(p[:, 1], e.sum(axis=1), 1e-300) < 1e-7
+    assert np.allclose(p[:, 2], (e * g["du"][:, :, 0].T).sum(axis=1), rtol=1e-6, atol=1e-9)
+    assert np.allclose(p[:, 4], g["du"][:, :, 0].sum(axis=0), rtol=1e-9, atol=1e-9)
+
+
+def test_shards_compose_to_the_full_job(gpu_pkg):
+    """Two half-size handles (as two ranks would hold) see the same noise and produce partials whose merge
+    equals the full job's partials."""
+    hor, dt, K = 0.64, 0.01, 512
+    full = make_gpu(gpu_pkg, hor, dt, K)
+    halves = [make_gpu(gpu_pkg, hor, dt, K // 2, rollout_offset=i * K // 2, rollouts_total=K) for i in range(2)]
+    P = gpu_pkg.Pose(theta=0.1, x=0.0, y=0.0)
+    for m in [full] + halves:
+        m.seed(5)
+        m.setCapture(True)
+        m.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.2))
+        m.newControls(P)
+    assert np.array_equal(np.concatenate([h.noise() for h in halves]), full.noise())
+    assert np.array_equal(np.concatenate([h.states() for h in halves]), full.states())
+    pf = full.partials()
+    ph = [h.partials() for h in halves]
+    m = np.minimum(ph[0][:, 0], ph[1][:, 0])
+    f = [np.exp((m - p[:, 0]) / 0.01) for p in ph]
+    assert np.allclose(m, pf[:, 0], rtol=1e-15)
+    for j in (1, 2, 3):
+        assert np.allclose(ph[0][:, j] * f[0] + ph[1][:, j] * f[1], pf[:, j], rtol=1e-9, atol=1e-12)
+    for j in (4, 5):
+        assert np.allclose(ph[0][:, j] + ph[1][:, j], pf[:, j], rtol=1e-9, atol=1e-9)
+
+
+def test_zero_variance_leaves_the_plan_alone(gpu_pkg):
+    prm = dict(orc.SHIPPED, ul_var=0.0, ur_var=0.0)
+    gpu = make_gpu(gpu_pkg, 0.64, 0.01, 64, prm)
+    gpu.setInitialControls(0.5, -0.25)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.0))
+    v = gpu.newControls(gpu_pkg.Pose())
+    assert (v.ul, v.ur) == (0.5, -0.25)
+    assert np.array_equal(gpu.plan(), np.repeat([[0.5], [-0.25]], 64, axis=1))
+
+
+def test_controls_saturate(gpu_pkg):
+    prm = dict(orc.SHIPPED, max_wheel_vel=0.05)
+    gpu = make_gpu(gpu_pkg, 0.64, 0.01, 256, prm)
+    gpu.seed(1)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=0.0, x=5.0, y=0.0))
+    for _ in range(3):
+        v = gpu.newControls(gpu_pkg.Pose())
+        assert abs(v.ul) <= 0.05 and abs(v.ur) <= 0.05
+    assert np.max(np.abs(gpu.plan())) <= 0.05
+
+
+def test_set_initial_controls_fills_plan_and_tail(gpu_pkg):
+    gpu = make_gpu(gpu_pkg, 0.5, 0.02, 32)
+    gpu.setInitialControls(1.5, -0.5)                    # mppi.cpp:54-61
+    assert np.array_equal(gpu.plan(), np.repeat([[1.5], [-0.5]], 25, axis=1))
+    gpu.seed(3)
+    gpu.newControls(gpu_pkg.Pose())
+    p = gpu.plan()
+    assert p[0, -1] == 1.5 and p[1, -1] == -0.5          # mppi.cpp:136-137
+
+
+def test_async_queue_equals_synchronous_calls(gpu_pkg):
+    a = make_gpu(gpu_pkg, 0.64, 0.01, 256)
+    b = make_gpu(gpu_pkg, 0.64, 0.01, 256)
+    P = gpu_pkg.Pose(theta=0.2, x=0.1, y=-0.1)
+    for m in (a, b):
+        m.seed(11)
+        m.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.0))
+    for _ in range(5):
+        va = a.newControls(P)
+    for _ in range(5):
+        b.enqueue(P)
+    vb = b.wait()
+    assert (va.ul, va.ur) == (vb.ul, vb.ur)
+    assert np.array_equal(a.plan(), b.plan())
+
+
+def test_state_ring_and_launch_count(gpu_pkg):
+    gpu = make_gpu(gpu_pkg, 0.64, 0.01, 128)
+    gpu.setStateRing(3)
+    gpu.seed(2)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.0))
+    n0 = gpu.launchCount()
+    first = None
+    for i in range(4):
+        gpu.newControls(gpu_pkg.Pose())
+        if i == 0:
+            first = gpu.states().copy()
+    assert gpu.launchCount() - n0 == 8                   # rollout + update per call
+    assert not np.array_equal(first, gpu.states())
+
+
+def test_error_behaviour(gpu_pkg):
+    B2NError = gpu_pkg.B2NError
+    with pytest.raises(IndexError):                      # reference: std::out_of_range from .at(), mppi.hpp:66-79
+        gpu_pkg.LossFunc([1.0, 1.0], [1.0, 1.0], [1.0, 1.0, 1.0])
+    with pytest.raises(B2NError) as e:
+        make_gpu(gpu_pkg, 0.64, 0.01, 0)
+    assert e.value.code == -1
+    with pytest.raises(B2NError) as e:
+        make_gpu(gpu_pkg, 2.57, 0.01, 8)                 # 257 steps
+    assert e.value.code == -4
+    gpu = make_gpu(gpu_pkg, 0.64, 0.01, 8)
+    with pytest.raises(B2NError):
+        gpu.costToGo()                                   # capture was not switched on
+    with pytest.raises(B2NError):
+        gpu.setNoise(np.zeros((8, 63, 2)))
