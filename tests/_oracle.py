@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle_nav.so")
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_nav.so")
+REF_SO = os.environ.get("B2N_REF_SO", os.path.join(ROOT, "oracle", "_ref", "libref_nav.so"))
 D = C.c_double
 nd = np.ctypeslib.ndpointer
 
@@ -36,9 +36,20 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def _preload_cxx_runtime():
+    """libref_nav.so prints through std::cout inside the reference's hot path; when libstdc++ first entered the
+    process RTLD_LOCAL (as a dependency of numpy) those iostream objects resolve to a second, uninitialised copy and
+    the first `std::cout <<` crashes.  Making the runtime global before loading the checkers avoids that."""
+    try:
+        C.CDLL("libstdc++.so.6", mode=C.RTLD_GLOBAL)
+    except OSError:
+        pass
+
+
 def oracle_lib():
     global _olib
     if _olib is None:
+        _preload_cxx_runtime()
         L = C.CDLL(ORACLE_SO)
         L.orc_mppi_create.restype = C.c_void_p
         L.orc_mppi_create.argtypes = [C.POINTER(_P)]
@@ -64,6 +75,7 @@ def oracle_lib():
 def ref_lib():
     global _rlib
     if _rlib is None:
+        _preload_cxx_runtime()
         L = C.CDLL(REF_SO)
         L.ref_rigid2d_seed.argtypes = [C.c_uint64]
         L.ref_bmapping_seed.argtypes = [C.c_uint64]
@@ -206,3 +218,430 @@ def unicycle_step(pose, ul, ur, dt, r=0.033, L=0.16):
     if abs(w) < 1e-12:
         return (x + v * dt * np.cos(th), y + v * dt * np.sin(th), th)
     return (x + v / w * (np.sin(th + w * dt) - np.sin(th)), y - v / w * (np.cos(th + w * dt) - np.cos(th)), th + w * dt)
+
+
+# =========================================================================================== RBPF
+# bmapping/launch/slam.launch:19-42 + bmapping/config/LDS_01_lidar.yaml, with the synthetic-bench
+# changes of SURVEY.md 8d (10 m map -> 200x200 cells, motion noise raised so that weights diverge)
+PF_SHIPPED = dict(
+    beam_min=0.0, beam_max=float(np.float32(np.deg2rad(360.0))), beam_delta=float(np.float32(np.deg2rad(1.0))),
+    range_min=0.12, range_max=3.5, z_hit=0.95, z_short=0.0, z_max=0.04, z_rand=0.01, sigma_hit=0.5,
+    resolution=0.05, xmin=-5.0, xmax=5.0, ymin=-5.0, ymax=5.0,
+    num_particles=40, k=50, srr=0.01, srt=0.02, str_=0.01, stt=0.02,
+    motion_noise=(1e-4, 1e-4, 1e-4), sample_range=(1e-4, 1e-4, 1e-4),
+    scan_min=1.0, scan_max=20.0, pose_min=1.0, pose_max=10.0, init_pose=(0.0, 0.0, 0.0))
+
+
+class _OPF(C.Structure):
+    _fields_ = [("beam_min", C.c_float), ("beam_max", C.c_float), ("beam_delta", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("z_hit", D), ("z_short", D), ("z_max", D), ("z_rand", D), ("sigma_hit", D),
+                ("resolution", D), ("xmin", D), ("xmax", D), ("ymin", D), ("ymax", D),
+                ("num_particles", C.c_int32), ("k", C.c_int32), ("srr", D), ("srt", D), ("str_", D), ("stt", D),
+                ("motion_noise", D * 3), ("sample_range", D * 3), ("scan_min", D), ("scan_max", D), ("pose_min", D),
+                ("pose_max", D), ("init_pose", D * 3)]
+
+
+def pf_params(**kw):
+    q = dict(PF_SHIPPED)
+    q.update(kw)
+    q["k"], q["num_particles"] = int(q["k"]), int(q["num_particles"])
+    return q
+
+
+_opf_bound = False
+_rpf_bound = False
+F32P = nd(np.float32)
+F64P = nd(np.float64)
+I32P = nd(np.int32)
+
+
+def _bind_oracle_pf():
+    global _opf_bound
+    L = oracle_lib()
+    if _opf_bound:
+        return L
+    L.orc_pf_create.restype = C.c_void_p
+    L.orc_pf_create.argtypes = [C.POINTER(_OPF)]
+    L.orc_pf_destroy.argtypes = [C.c_void_p]
+    L.orc_pf_noise_mt19937.argtypes = [C.c_void_p, C.c_uint64]
+    L.orc_pf_noise_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    L.orc_pf_noise_external.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_pf_set_shard.argtypes = [C.c_void_p, C.c_int]
+    L.orc_pf_grid_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_pf_slam.argtypes = [C.c_void_p, F32P, C.c_int, F64P, F64P, F64P, C.c_int, F64P]
+    L.orc_pf_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_pf_set_weights.argtypes = [C.c_void_p, F64P]
+    L.orc_pf_set_poses.argtypes = [C.c_void_p, F64P]
+    L.orc_pf_get_resample.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.orc_pf_normalize_resample.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    L.orc_pf_robot_state.argtypes = [C.c_void_p, F64P]
+    L.orc_pf_new_map.argtypes = [C.c_void_p, nd(np.int8)]
+    L.orc_pf_grid_dump.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.orc_pf_grid_occ_order.argtypes = [C.c_void_p, C.c_int, I32P, C.c_int]
+    L.orc_pf_grid_bucket_count.argtypes = [C.c_void_p, C.c_int]
+    L.orc_pf_grid_likelihood.argtypes = [C.c_void_p, C.c_int, F32P, C.c_int, F64P, C.POINTER(D)]
+    L.orc_pf_grid_integrate.argtypes = [C.c_void_p, C.c_int, F32P, C.c_int, F64P]
+    L.orc_pf_grid_end_points.argtypes = [C.c_void_p, C.c_int, F32P, C.c_int, F64P, F64P]
+    L.orc_pf_grid_free_cells.argtypes = [C.c_void_p, C.c_int, F64P, F64P, I32P, C.c_int]
+    L.orc_pf_grid_map.argtypes = [C.c_void_p, C.c_int, nd(np.int8)]
+    L.orc_pf_grid_stats.argtypes = [C.c_void_p, C.c_int, nd(np.uint64)]
+    L.orc_selftest_occset.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    L.orc_selftest_heap.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    _opf_bound = True
+    return L
+
+
+def _bind_ref_pf():
+    global _rpf_bound
+    L = ref_lib()
+    if _rpf_bound:
+        return L
+    F5, D5 = C.c_float * 5, D * 5
+    L.ref_grid_create.restype = C.c_void_p
+    L.ref_grid_create.argtypes = [F5, D5, D, D, D, D, D]
+    L.ref_grid_destroy.argtypes = [C.c_void_p]
+    L.ref_grid_clone.restype = C.c_void_p
+    L.ref_grid_clone.argtypes = [C.c_void_p]
+    L.ref_grid_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ref_grid_likelihood.argtypes = [C.c_void_p, F32P, C.c_int, F64P, C.POINTER(D)]
+    L.ref_grid_integrate.argtypes = [C.c_void_p, F32P, C.c_int, F64P]
+    L.ref_grid_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    L.ref_grid_occ_order.argtypes = [C.c_void_p, I32P, C.c_int]
+    L.ref_grid_bucket_count.argtypes = [C.c_void_p]
+    L.ref_grid_map.argtypes = [C.c_void_p, nd(np.int8)]
+    L.ref_grid_end_points.argtypes = [C.c_void_p, F32P, C.c_int, F64P, F64P]
+    L.ref_grid_free_cells.argtypes = [C.c_void_p, F64P, F64P, I32P, C.c_int]
+    L.ref_pf_create.restype = C.c_void_p
+    L.ref_pf_create.argtypes = [C.c_int, C.c_int, D * 14, F5, D5, D, D, D, D, D, D * 3]
+    L.ref_pf_destroy.argtypes = [C.c_void_p]
+    L.ref_pf_set_icp.argtypes = [C.c_int, F64P]
+    L.ref_pf_slam.argtypes = [C.c_void_p, F32P, C.c_int, F64P, F64P, F64P, C.POINTER(C.c_int)]
+    L.ref_pf_num.argtypes = [C.c_void_p]
+    L.ref_pf_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_pf_set_weights.argtypes = [C.c_void_p, F64P]
+    L.ref_pf_grid_dump.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.ref_pf_grid_occ_order.argtypes = [C.c_void_p, C.c_int, I32P, C.c_int]
+    L.ref_pf_robot_state.argtypes = [C.c_void_p, F64P]
+    L.ref_pf_new_map.argtypes = [C.c_void_p, nd(np.int8)]
+    L.ref_pf_normalize_resample.argtypes = [C.c_void_p, C.POINTER(C.c_int), I32P]
+    _rpf_bound = True
+    return L
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class _PfCommon:
+    """Shared convenience over either CPU particle filter (same method names on both)."""
+
+    def grid(self, particle=0):
+        G = self.G
+        out = dict(log_odds=np.zeros(G), prob=np.zeros(G), occ_dist=np.zeros(G), state=np.zeros(G, dtype=np.int32))
+        self._grid_dump(particle, out)
+        return out
+
+    def state(self):
+        N = self.N
+        w, p, pp = np.zeros(N), np.zeros((N, 3)), np.zeros((N, 3))
+        self._get(w, p, pp)
+        return dict(weights=w, poses=p, prev_poses=pp)
+
+
+class OraclePf(_PfCommon):
+    """oracle/liboracle_nav.so restatement of bmapping::ParticleFilter (+ per-particle GridMapper)."""
+
+    def __init__(self, **kw):
+        self.L = _bind_oracle_pf()
+        q = pf_params(**kw)
+        self.q = q
+        p = _OPF(q["beam_min"], q["beam_max"], q["beam_delta"], q["range_min"], q["range_max"], q["z_hit"], q["z_short"],
+                 q["z_max"], q["z_rand"], q["sigma_hit"], q["resolution"], q["xmin"], q["xmax"], q["ymin"], q["ymax"],
+                 q["num_particles"], q["k"], q["srr"], q["srt"], q["str_"], q["stt"], (D * 3)(*q["motion_noise"]),
+                 (D * 3)(*q["sample_range"]), q["scan_min"], q["scan_max"], q["pose_min"], q["pose_max"],
+                 (D * 3)(*q["init_pose"]))
+        self.h = C.c_void_p(self.L.orc_pf_create(C.byref(p)))
+        self.N = q["num_particles"]
+        xs, ys = C.c_int(), C.c_int()
+        self.G = self.L.orc_pf_grid_size(self.h, C.byref(xs), C.byref(ys))
+        self.xsize, self.ysize = xs.value, ys.value
+        self._ext = None
+
+    def noise_mt19937(self, seed):
+        self.L.orc_pf_noise_mt19937(self.h, seed)
+
+    def noise_philox(self, seed, first_call=0):
+        self.L.orc_pf_noise_philox(self.h, seed, first_call)
+
+    def noise_external(self, z, per_particle):
+        self._ext = _f64(z)
+        assert self._ext.size == self.N * per_particle + 1
+        self.L.orc_pf_noise_external(self.h, _vp(self._ext), per_particle)
+
+    def set_shard(self, offset):
+        self.L.orc_pf_set_shard(self.h, offset)
+
+    def slam(self, scan, twist, cur_odom, prev_odom, icp_ok=0, icp_pose=(0.0, 0.0, 0.0)):
+        scan = _f32(scan)
+        return self.L.orc_pf_slam(self.h, scan, scan.size, _f64(twist), _f64(cur_odom), _f64(prev_odom), int(icp_ok), _f64(icp_pose))
+
+    def _get(self, w, p, pp):
+        self.L.orc_pf_get(self.h, _vp(w), _vp(p), _vp(pp))
+
+    def set_weights(self, w):
+        self.L.orc_pf_set_weights(self.h, _f64(w))
+
+    def set_poses(self, p):
+        self.L.orc_pf_set_poses(self.h, _f64(p))
+
+    def resample_info(self):
+        neff, rs = C.c_int(), C.c_int()
+        anc = np.zeros(self.N, dtype=np.int32)
+        self.L.orc_pf_get_resample(self.h, C.byref(neff), C.byref(rs), _vp(anc))
+        return neff.value, rs.value, anc
+
+    def normalize_resample(self):
+        rs = C.c_int()
+        anc = np.zeros(self.N, dtype=np.int32)
+        self.L.orc_pf_normalize_resample(self.h, C.byref(rs), _vp(anc))
+        return rs.value, anc
+
+    def robot_state(self):
+        out = np.zeros(3)
+        self.L.orc_pf_robot_state(self.h, out)
+        return out
+
+    def new_map(self):
+        out = np.zeros(self.G, dtype=np.int8)
+        self.L.orc_pf_new_map(self.h, out)
+        return out
+
+    def _grid_dump(self, particle, out):
+        self.L.orc_pf_grid_dump(self.h, particle, _vp(out["log_odds"]), _vp(out["prob"]), _vp(out["occ_dist"]), _vp(out["state"]))
+
+    def occ_order(self, particle=0):
+        keys = np.zeros(self.G, dtype=np.int32)
+        n = self.L.orc_pf_grid_occ_order(self.h, particle, keys, self.G)
+        return keys[:n].copy()
+
+    def bucket_count(self, particle=0):
+        return self.L.orc_pf_grid_bucket_count(self.h, particle)
+
+    def grid_likelihood(self, scan, pose, particle=0):
+        scan = _f32(scan)
+        p = D()
+        rc = self.L.orc_pf_grid_likelihood(self.h, particle, scan, scan.size, _f64(pose), C.byref(p))
+        return rc, p.value
+
+    def grid_integrate(self, scan, pose, particle=0):
+        scan = _f32(scan)
+        return self.L.orc_pf_grid_integrate(self.h, particle, scan, scan.size, _f64(pose))
+
+    def grid_end_points(self, scan, pose, particle=0):
+        scan = _f32(scan)
+        xy = np.zeros((scan.size, 2))
+        n = self.L.orc_pf_grid_end_points(self.h, particle, scan, scan.size, _f64(pose), xy)
+        return xy[:n].copy()
+
+    def grid_free_cells(self, pt, pose, particle=0):
+        cells = np.zeros(4 * (self.xsize + self.ysize), dtype=np.int32)
+        n = self.L.orc_pf_grid_free_cells(self.h, particle, _f64(pt), _f64(pose), cells, cells.size)
+        return None if n < 0 else cells[:n].copy()
+
+    def grid_map(self, particle=0):
+        out = np.zeros(self.G, dtype=np.int8)
+        self.L.orc_pf_grid_map(self.h, particle, out)
+        return out
+
+    def grid_stats(self, particle=0):
+        out = np.zeros(4, dtype=np.uint64)
+        self.L.orc_pf_grid_stats(self.h, particle, out)
+        return dict(ray_cells=int(out[0]), esdf_iterations=int(out[1]), esdf_pushes=int(out[2]), heap_max=int(out[3]))
+
+    def __del__(self):
+        try:
+            self.L.orc_pf_destroy(self.h)
+        except Exception:
+            pass
+
+
+def _laser_arrays(q):
+    lf = (C.c_float * 5)(q["beam_min"], q["beam_max"], q["beam_delta"], q["range_min"], q["range_max"])
+    ld = (D * 5)(q["z_hit"], q["z_short"], q["z_max"], q["z_rand"], q["sigma_hit"])
+    return lf, ld
+
+
+class RefPf(_PfCommon):
+    """The compiled reference bmapping::ParticleFilter.  RNG = the process-global bmapping engine; the ICP
+    outcome is injected (process-global too), see oracle/ref_capi.cpp."""
+
+    def __init__(self, **kw):
+        self.L = _bind_ref_pf()
+        q = pf_params(**kw)
+        self.q = q
+        lf, ld = _laser_arrays(q)
+        pfp = (D * 14)(q["srr"], q["srt"], q["str_"], q["stt"], *q["motion_noise"], *q["sample_range"], q["scan_min"],
+                       q["scan_max"], q["pose_min"], q["pose_max"])
+        self.h = C.c_void_p(self.L.ref_pf_create(q["num_particles"], q["k"], pfp, lf, ld, q["resolution"], q["xmin"],
+                                                 q["xmax"], q["ymin"], q["ymax"], (D * 3)(*q["init_pose"])))
+        self.N = q["num_particles"]
+        self.xsize = self.ysize = int(np.ceil((q["xmax"] - q["xmin"]) / q["resolution"]))
+        self.G = self.xsize * self.ysize
+
+    def seed(self, s):
+        self.L.ref_bmapping_seed(s)
+
+    def slam(self, scan, twist, cur_odom, prev_odom, icp_ok=0, icp_pose=(0.0, 0.0, 0.0)):
+        scan = _f32(scan)
+        self.L.ref_pf_set_icp(int(icp_ok), _f64(icp_pose))
+        rs = C.c_int()
+        rc = self.L.ref_pf_slam(self.h, scan, scan.size, _f64(twist), _f64(cur_odom), _f64(prev_odom), C.byref(rs))
+        self.last_resampled = rs.value
+        return rc
+
+    def _get(self, w, p, pp):
+        self.L.ref_pf_get(self.h, _vp(w), _vp(p), _vp(pp))
+
+    def set_weights(self, w):
+        self.L.ref_pf_set_weights(self.h, _f64(w))
+
+    def normalize_resample(self):
+        rs = C.c_int()
+        anc = np.zeros(self.N, dtype=np.int32)
+        self.L.ref_pf_normalize_resample(self.h, C.byref(rs), anc)
+        return rs.value, anc
+
+    def robot_state(self):
+        out = np.zeros(3)
+        self.L.ref_pf_robot_state(self.h, out)
+        return out
+
+    def new_map(self):
+        out = np.zeros(self.G, dtype=np.int8)
+        self.L.ref_pf_new_map(self.h, out)
+        return out
+
+    def _grid_dump(self, particle, out):
+        self.L.ref_pf_grid_dump(self.h, particle, _vp(out["log_odds"]), _vp(out["prob"]), _vp(out["occ_dist"]), _vp(out["state"]))
+
+    def occ_order(self, particle=0):
+        keys = np.zeros(self.G, dtype=np.int32)
+        n = self.L.ref_pf_grid_occ_order(self.h, particle, keys, self.G)
+        return keys[:n].copy()
+
+    def __del__(self):
+        try:
+            self.L.ref_pf_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RefGrid:
+    """A stand-alone compiled reference bmapping::GridMapper."""
+
+    def __init__(self, **kw):
+        self.L = _bind_ref_pf()
+        q = pf_params(**kw)
+        lf, ld = _laser_arrays(q)
+        self.h = C.c_void_p(self.L.ref_grid_create(lf, ld, q["resolution"], q["xmin"], q["xmax"], q["ymin"], q["ymax"]))
+        xs, ys = C.c_int(), C.c_int()
+        self.G = self.L.ref_grid_size(self.h, C.byref(xs), C.byref(ys))
+        self.xsize, self.ysize = xs.value, ys.value
+
+    def likelihood(self, scan, pose):
+        scan = _f32(scan)
+        p = D()
+        rc = self.L.ref_grid_likelihood(self.h, scan, scan.size, _f64(pose), C.byref(p))
+        return rc, p.value
+
+    def integrate(self, scan, pose):
+        scan = _f32(scan)
+        return self.L.ref_grid_integrate(self.h, scan, scan.size, _f64(pose))
+
+    def grid(self):
+        G = self.G
+        out = dict(log_odds=np.zeros(G), prob=np.zeros(G), occ_dist=np.zeros(G), state=np.zeros(G, dtype=np.int32))
+        self.L.ref_grid_dump(self.h, _vp(out["log_odds"]), _vp(out["prob"]), _vp(out["occ_dist"]), _vp(out["state"]))
+        return out
+
+    def occ_order(self):
+        keys = np.zeros(self.G, dtype=np.int32)
+        n = self.L.ref_grid_occ_order(self.h, keys, self.G)
+        return keys[:n].copy()
+
+    def bucket_count(self):
+        return self.L.ref_grid_bucket_count(self.h)
+
+    def grid_map(self):
+        out = np.zeros(self.G, dtype=np.int8)
+        self.L.ref_grid_map(self.h, out)
+        return out
+
+    def end_points(self, scan, pose):
+        scan = _f32(scan)
+        xy = np.zeros((scan.size, 2))
+        n = self.L.ref_grid_end_points(self.h, scan, scan.size, _f64(pose), xy)
+        return xy[:n].copy()
+
+    def free_cells(self, pt, pose):
+        cells = np.zeros(4 * (self.xsize + self.ysize), dtype=np.int32)
+        n = self.L.ref_grid_free_cells(self.h, _f64(pt), _f64(pose), cells, cells.size)
+        return None if n < 0 else cells[:n].copy()
+
+    def __del__(self):
+        try:
+            self.L.ref_grid_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------ synthetic world ---
+def room_scan(pose, half=2.5, boxes=((0.8, 1.4, -0.3, 0.4),), n_beams=360, beam_delta=np.deg2rad(1.0), sigma=0.01, rng=None,
+              range_max=3.5):
+    """Analytic ray cast from pose = (theta, x, y) in an axis-aligned square room of half-width `half` with
+    axis-aligned boxes (xlo, xhi, ylo, yhi); Gaussian range noise sigma (Gazebo lidar,
+    nuturtle_gazebo/urdf/diff_drive.gazebo.xacro:101-105); float32 ranges; beams past range_max read range_max + 1
+    (filtered by the range gate like an LDS-01 'inf')."""
+    th, x, y = pose
+    out = np.zeros(n_beams, dtype=np.float32)
+    for b in range(n_beams):
+        a = th + b * beam_delta
+        dx, dy = np.cos(a), np.sin(a)
+        best = np.inf
+        rects = [(-half, half, -half, half)] + list(boxes)
+        for (xl, xh, yl, yh) in rects:
+            for (px, horiz) in ((xl, False), (xh, False), (yl, True), (yh, True)):
+                if not horiz:
+                    if abs(dx) < 1e-12:
+                        continue
+                    t = (px - x) / dx
+                    q = y + t * dy
+                    ok = yl - 1e-12 <= q <= yh + 1e-12
+                else:
+                    if abs(dy) < 1e-12:
+                        continue
+                    t = (px - y) / dy
+                    q = x + t * dx
+                    ok = xl - 1e-12 <= q <= xh + 1e-12
+                if ok and t > 1e-9 and t < best:
+                    best = t
+        r = best + (rng.normal(0.0, sigma) if (rng is not None and sigma > 0) else 0.0)
+        out[b] = np.float32(r if r < range_max else range_max + 1.0)
+    return out
+
+
+def circle_path(n_scans, radius=0.5, step=0.05):
+    """Robot poses (theta, x, y) on a circle of `radius`, arc length `step` per scan, heading tangent; with the
+    per-scan body twist (w, vx, vy) that takes one pose to the next."""
+    poses, twists = [], []
+    dphi = step / radius
+    for i in range(n_scans + 1):
+        phi = i * dphi
+        poses.append((np.pi / 2 + phi, radius * np.cos(phi), radius * np.sin(phi)))
+    for i in range(n_scans):
+        twists.append((dphi, step, 0.0))
+    return np.array(poses), np.array(twists)
