@@ -167,8 +167,10 @@ int b2n_pf_get_robot_state(b2n_pf *h, double pose[3]);
 int b2n_pf_new_map(b2n_pf *h, int8_t *out, size_t count);
 
 int b2n_pf_seed(b2n_pf *h, uint64_t seed, uint32_t first_call);
-/* standard normals for the NEXT call only: z[n][3] motion draws per particle (theta, x, y order),
- * then one more value for the resampling draw: count = 3*N + 1 */
+/* standard normals for the NEXT call only, in the order the reference draws them per particle
+ * (bmapping::sampleStandardNormal, particle_filter.cpp:25-36): motion-model branch z[n][3] (theta, x, y);
+ * proposal branch z[n][3*(k+1)] (k mode samples, then the new pose); then ONE more value, the resampling
+ * draw (used only if the filter resamples): count = 3*N + 1 or 3*(k+1)*N + 1 */
 int b2n_pf_set_noise(b2n_pf *h, const double *z, size_t count);
 
 /* Taps */
@@ -180,16 +182,34 @@ int b2n_pf_set_poses(b2n_pf *h, const double *poses, size_t count);
 /* outcome of the last SLAM(): N_eff as the reference prints it, whether it resampled, and the
  * ancestor of every slot (identity when it did not) */
 int b2n_pf_get_resample(b2n_pf *h, int *neff, int *resampled, int32_t *ancestors, size_t count);
-/* one particle's map: log-odds (fp64), distance to nearest occupied cell (fp32), class (-1/0/1) */
-int b2n_pf_get_grid(b2n_pf *h, int particle, double *log_odds, float *occ_dist, int8_t *state, size_t count);
-int b2n_pf_set_grid(b2n_pf *h, int particle, const double *log_odds, const float *occ_dist, const int8_t *state,
-                    const int32_t *occ_order, int n_occ, size_t count);
-/* iteration order of the occupied-cell set (seeds of the distance transform), returns the count */
+/* one particle's map: log-odds, distance to the obstacle cell that claimed the cell (grid_mapper.hpp Cell::occ_dist,
+ * reconstructed exactly as sqrt(di^2 + dj^2) * resolution), class (-1 unknown / 0 free / 1 occupied) */
+int b2n_pf_get_grid(b2n_pf *h, int particle, double *log_odds, double *occ_dist, int8_t *state, size_t count);
+/* iteration order of the particle's occupied-cell set (std::unordered_set<int> occ_cells_, the seeds of the
+ * distance transform, grid_mapper.cpp:348-361); writes up to cap keys, *n_occ = size of the set */
 int b2n_pf_get_occ_order(b2n_pf *h, int particle, int32_t *keys, size_t cap, int *n_occ);
 /* run only parts of SLAM(), for parity tests and kernel timing */
 int b2n_pf_likelihoods(b2n_pf *h, const float *scan, int n_beams, double *out, size_t count);
+/* normalizeWeights + effectiveParticles + lowVarianceResampling alone (particle_filter.cpp:244-249) */
+int b2n_pf_normalize_resample(b2n_pf *h);
 int b2n_pf_set_stream(b2n_pf *h, void *cuda_stream);
 int b2n_pf_launch_count(const b2n_pf *h, uint64_t *launches);
+/* CUDA-event durations (ms) of the last SLAM(): [0] sample + weight + ray integration, [1] distance field,
+ * [2] normalise + resample + particle copies */
+int b2n_pf_set_kernel_timing(b2n_pf *h, int on);
+int b2n_pf_kernel_times(b2n_pf *h, double ms[3]);
+/* brushfire iterations summed over all particles and calls, largest heap seen */
+int b2n_pf_distance_field_stats(b2n_pf *h, uint64_t *iterations, uint64_t *heap_max);
+/* heap entries kept in shared memory per particle in flight (the rest spills to global memory); default 2048 */
+int b2n_pf_set_heap_capacity(b2n_pf *h, int entries);
+/* what create() derives on the HOST from the constructor arguments, without needing a device (CPU tests):
+ * constants = {t_occ, t_free, d_free, d_occ} - the log-odds thresholds equivalent to GridMapper::updateCellState's
+ * prob >= 0.9 / prob <= 0.35 under this host's exp(), and the two log-odds steps (grid_mapper.cpp:42-47,438-477);
+ * beam_cs[beam_count] = cos, sin of LaserScanner's accumulated beam angles (sensor_model.cpp:66-108);
+ * pz = likelihood term z_hit * pdfNormal(sqrt(d2) * res, sigma_hit^2) + z_rand / z_max for every squared cell distance
+ * d2 the distance field can hold, last entry = never-reached cell (grid_mapper.cpp:101-128) */
+int b2n_pf_host_tables(const b2n_pf_params *params, double constants[4], double *beam_cs, size_t beam_count, double *pz,
+                       size_t pz_cap, int *pz_n);
 int b2n_pf_comm_init(b2n_pf *h, int rank, int nranks, const void *unique_id128);
 
 #ifdef __cplusplus

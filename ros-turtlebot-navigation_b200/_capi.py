@@ -92,11 +92,16 @@ PROTOTYPES = {
     "b2n_pf_set_poses": (C.c_int, [_vp, _vp, _sz]),
     "b2n_pf_get_resample": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int), _vp, _sz]),
     "b2n_pf_get_grid": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz]),
-    "b2n_pf_set_grid": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _sz]),
     "b2n_pf_get_occ_order": (C.c_int, [_vp, C.c_int, _vp, _sz, _P(C.c_int)]),
     "b2n_pf_likelihoods": (C.c_int, [_vp, _vp, C.c_int, _vp, _sz]),
+    "b2n_pf_normalize_resample": (C.c_int, [_vp]),
     "b2n_pf_set_stream": (C.c_int, [_vp, _vp]),
     "b2n_pf_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "b2n_pf_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
+    "b2n_pf_kernel_times": (C.c_int, [_vp, _P(D)]),
+    "b2n_pf_distance_field_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
+    "b2n_pf_set_heap_capacity": (C.c_int, [_vp, C.c_int]),
+    "b2n_pf_host_tables": (C.c_int, [_P(PfParams), _P(D), _vp, _sz, _vp, _sz, _P(C.c_int)]),
     "b2n_pf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
 }
 

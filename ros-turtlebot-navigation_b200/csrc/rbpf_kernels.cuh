@@ -1,0 +1,850 @@
+// rbpf_kernels.cuh - bmapping::ParticleFilter::SLAM() as sm_100a kernels (fallback and improved-proposal
+// branches, map integration, distance field, normalise / resample, map export).
+//
+// Reference path (all under /root/reference): bmapping/src/bmapping/particle_filter.cpp:141-251 (SLAM),
+// :295-322 (motion model), :383-437 (odometry likelihood), :442-500 (normalise, N_eff, low-variance walk),
+// :504-599 (improved proposal); bmapping/src/bmapping/grid_mapper.cpp:69-133 (likelihood field), :140-182
+// (integrateScan), :272-435 (brushfire distance field), :438-546 (cell state + occupied set), :549-898
+// (Bresenham, indexing), :185-226 (map export); bmapping/src/bmapping/sensor_model.cpp:43-112 (end points).
+//
+// This translation unit is compiled with -fmad=false: every a*b+c below is two IEEE operations, like the
+// reference's x86-64 build, because cell indices and resampling ancestors have to come out bit-exact.
+//
+// Design (DESIGN.md "RBPF"):
+//   * ONE WARP PER PARTICLE.  Lanes stride the beams for end points and likelihood terms; the product of the
+//     per-beam terms is then taken in beam order (the reference's rounding) by a redundant-lane loop.
+//   * per-particle map = SoA planes in HBM: log-odds fp64 [N][G], squared cell distance to the claimed obstacle
+//     u32 [N][G] (occ_dist = sqrt(d2) * resolution exactly; the likelihood term of every possible d2 is a
+//     host-built table, its head staged into shared memory by TMA together with the beam sin/cos table),
+//     plus the occupied set in libstdc++ unordered_set layout (node list + bucket heads, u16) because its
+//     ITERATION ORDER seeds the distance transform.
+//   * rays are applied in beam order, 32 cells of a ray at a time (cells of one ray are distinct; the k-th cell
+//     of the reference's Bresenham variants has a closed form), hash events replayed in lane order.
+//   * the distance field is the reference's order-dependent brushfire: binary heap (libstdc++ push_heap /
+//     pop_heap mechanics, ties included) and visit marks live in shared memory; every lane of the warp runs
+//     the heap code redundantly so that no intra-warp hand-off is needed; lanes 0-3 test the four neighbours.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2n
+{
+
+constexpr uint16_t kNil16 = 0xFFFFu;
+constexpr uint32_t kD2Unreached = 0xFFFFFFFFu;   // cell never claimed: occ_dist = max_occ_dist (grid_mapper.cpp:49,58)
+constexpr int kPfWarpsPerCta = 4;
+constexpr int kPfStatusOffMap = 1;               // reference: world2Grid / world2RowMajor throw
+constexpr int kPfStatusNumeric = 2;              // reference: "eta is 0" / zero variance in pdfNormal
+
+// bucket counts libstdc++'s _Prime_rehash_policy walks through when keys arrive one at a time
+__constant__ uint32_t kBucketChainDev[19] = {13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229,
+                                             172933, 351061, 712697, 1447153, 2938679, 5967347};
+
+struct PfParticle
+{
+  double pose[3], prev_pose[3];   // theta, x, y (particle_filter.cpp:133)
+  double weight;
+  uint32_t n_occ, bucket_count, next_resize;
+  int32_t chain;
+};
+
+struct PfPlanes
+{
+  double *log_odds;    // [N][G]
+  uint32_t *d2;        // [N][G]
+  uint16_t *nxt;       // [N][nxt_stride], slot G = before-begin
+  uint16_t *bkt;       // [N][bkt_stride]
+  PfParticle *meta;    // [N]
+};
+
+struct PfConst
+{
+  int N, G, xsize, ysize;
+  int gstride;                     // plane stride per particle (G rounded up to a multiple of 4)
+  int nxt_stride, bkt_stride;
+  int cell_radius;                 // grid_mapper.cpp:50
+  double xmin, xmax, ymin, ymax, res;
+  double range_min, range_max;     // floats of LaserProperties, promoted as the comparison in sensor_model.cpp:81 does
+  double t_occ, t_free;            // log-odds thresholds equivalent to prob >= 0.9 / prob <= 0.35 under the host's exp()
+  double d_free, d_occ;            // log_odds_free_ - log_odds_prior_, log_odds_occ_ - log_odds_prior_
+  const double *beam_cs;           // [max_beams][2] cos, sin of the accumulated beam angle (host libm)
+  const double *pz_table;          // [pz_n] z_hit * pdfNormal(sqrt(d2) * res, sigma^2) + z_rand / z_max; last = unreached
+  int pz_n, pz_stage;              // table length; entries staged in shared memory
+  double sig[3];                   // sqrt of the motion-noise variances (Cholesky of a diagonal matrix)
+  // improved proposal
+  int k_samples;
+  double sig_mode[3];
+  double srr, srt, str, stt;
+  double scan_min, scan_max, pose_min, pose_max;
+};
+
+struct PfCall
+{
+  const float *scan;
+  int n_beams;
+  double u_w, u_vx;                // body twist of the scan interval
+  double cur_od[3], prev_od[3];
+  int icp_ok;
+  double icp[3];                   // theta, x, y of Ticp
+  uint32_t seed_lo, seed_hi, call;
+  int particle_offset;
+  const double *ext;               // external standard normals [N][ext_per] + 1, or null
+  int ext_per;
+  int *status;                     // OR of kPfStatus*
+};
+
+// ---- small helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pf_almost_zero(double d) { return fabs(d - 0.0) < 1.0e-12; }   // rigid2d.hpp:24-27
+
+// rigid2d.hpp:52-64
+__device__ __forceinline__ double pf_normalize_angle_pi(double rad)
+{
+  const double PI = 3.14159265358979323846;
+  const double q = floor((rad + PI) / (2.0 * PI));
+  rad = (rad + PI) - q * 2.0 * PI;
+  if (rad < 0) rad += 2.0 * PI;
+  return rad - PI;
+}
+
+// grid_mapper.cpp:810-887 on one coordinate pair; false where the reference throws
+__device__ __forceinline__ bool pf_world2grid(const PfConst &c, double x, double y, int &gi, int &gj)
+{
+  if (!(x >= c.xmin && x <= c.xmax)) return false;
+  if (!(y >= c.ymin && y <= c.ymax)) return false;
+  double i = floor((x - c.xmin) / c.res);
+  if (i == (double)c.xsize) i -= 1.0;
+  double j = floor((y - c.ymin) / c.res);
+  if (j == (double)c.ysize) j -= 1.0;
+  gi = (int)i; gj = (int)j;
+  return true;
+}
+
+// one standard normal of particle `gid` (draw number d of this call); every lane computes the same value
+__device__ __forceinline__ double pf_std_normal(const PfCall &q, int local, int gid, int d)
+{
+  if (q.ext) return q.ext[(size_t)local * q.ext_per + d];
+  double z0, z1;
+  normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, (uint32_t)gid, (uint32_t)(d >> 1), z0, z1);
+  return (d & 1) ? z1 : z0;
+}
+
+// ---- the occupied set: std::unordered_set<int> in libstdc++ layout ------------------------------------------------
+struct OccSetDev
+{
+  uint16_t *nxt, *bkt;
+  uint32_t G, bucket_count, count, next_resize;
+  int chain;
+};
+
+// _Hashtable::_M_rehash_aux (unique keys).  Executed by every lane with identical data (same addresses, same
+// values), the bucket clear is shared out over the lanes.
+__device__ __forceinline__ void occ_rehash(OccSetDev &s, uint32_t n, int lane)
+{
+  for (uint32_t b = lane; b < n; b += 32) s.bkt[b] = kNil16;
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t p = s.nxt[s.G];
+    s.nxt[s.G] = kNil16;
+    uint32_t bbegin = 0;
+    while (p != kNil16) {
+      const uint32_t next = s.nxt[p];
+      const uint32_t b = p % n;
+      const uint32_t before = s.bkt[b];
+      if (before == kNil16) {
+        const uint32_t first = s.nxt[s.G];
+        s.nxt[p] = (uint16_t)first;
+        s.nxt[s.G] = (uint16_t)p;
+        s.bkt[b] = (uint16_t)s.G;
+        if (first != kNil16) s.bkt[bbegin] = (uint16_t)p;
+        bbegin = b;
+      } else {
+        s.nxt[p] = s.nxt[before];
+        s.nxt[before] = (uint16_t)p;
+      }
+      p = next;
+    }
+  }
+  s.bucket_count = n;
+  __syncwarp();
+}
+
+// _M_insert_unique_node for a key that is NOT present (caller checked membership through the log-odds)
+__device__ __forceinline__ void occ_insert(OccSetDev &s, uint32_t key, int lane)
+{
+  if (s.count + 1 > s.next_resize) {   // _Prime_rehash_policy::_M_need_rehash, max load factor 1
+    const uint32_t floor_bkts = s.next_resize ? (s.count + 1) : max(s.count + 1, 11u);
+    if (floor_bkts >= s.bucket_count) {
+      s.chain++;
+      const uint32_t n = kBucketChainDev[s.chain];
+      occ_rehash(s, n, lane);
+      s.next_resize = n;
+    } else {
+      s.next_resize = s.bucket_count;
+    }
+  }
+  if (lane == 0) {
+    const uint32_t b = key % s.bucket_count;
+    const uint32_t before = s.bkt[b];
+    if (before != kNil16) {
+      s.nxt[key] = s.nxt[before];
+      s.nxt[before] = (uint16_t)key;
+    } else {
+      const uint32_t first = s.nxt[s.G];
+      s.nxt[key] = (uint16_t)first;
+      s.nxt[s.G] = (uint16_t)key;
+      if (first != kNil16) s.bkt[first % s.bucket_count] = (uint16_t)key;
+      s.bkt[b] = (uint16_t)s.G;
+    }
+  }
+  s.count++;
+  __syncwarp();
+}
+
+// _M_erase(bkt, prev, node) for a key that IS present
+__device__ __forceinline__ void occ_erase(OccSetDev &s, uint32_t key, int lane)
+{
+  if (lane == 0) {
+    const uint32_t b = key % s.bucket_count;
+    const uint32_t head = s.bkt[b];
+    uint32_t prev = head;
+    while (s.nxt[prev] != key) prev = s.nxt[prev];
+    const uint32_t next = s.nxt[key];
+    if (prev == head) {
+      if (next == kNil16 || next % s.bucket_count != b) {
+        if (next != kNil16) s.bkt[next % s.bucket_count] = (uint16_t)head;
+        s.bkt[b] = kNil16;
+      }
+    } else if (next != kNil16) {
+      const uint32_t nb = next % s.bucket_count;
+      if (nb != b) s.bkt[nb] = (uint16_t)prev;
+    }
+    s.nxt[prev] = (uint16_t)next;
+    s.nxt[key] = kNil16;
+  }
+  s.count--;
+  __syncwarp();
+}
+
+// ---- end points and likelihood terms of one pose (sensor_model.cpp:43-112, grid_mapper.cpp:69-133) ------------------
+// Lanes stride the beams.  ep[b] = (i << 16 | j) of the end-point cell, or 0xFFFFFFFF for a gated-out beam;
+// pz[b] = likelihood term (only when want_pz).  Returns false (on every lane) if a valid end point is off the map.
+__device__ __forceinline__ bool pf_end_points(const PfConst &c, const float *scan, int n, const double *s_beam, const double *s_pz,
+                                              const uint32_t *d2_plane, double th, double x, double y, uint32_t *ep, double *pz,
+                                              bool want_pz, int lane)
+{
+  // Transform2D(Vector2D(x, y), theta) then pose * Trs with Trs = identity (rigid2d.cpp:154-166,221-231):
+  // x = c*0 - s*0 + x, y = s*0 + c*0 + y, theta += 0, cos/sin recomputed from the same theta
+  double st, ct;
+  sincos(th, &st, &ct);
+  const double tx = ct * 0.0 - st * 0.0 + x;
+  const double ty = st * 0.0 + ct * 0.0 + y;
+  bool ok = true;
+  for (int b = lane; b < n; b += 32) {
+    const double range = (double)scan[b];
+    uint32_t e = 0xFFFFFFFFu;
+    if (range >= c.range_min && range < c.range_max) {
+      const double px = range * s_beam[2 * b], py = range * s_beam[2 * b + 1];   // sensor_model.cpp:9-16
+      const double wx = ct * px - st * py + tx;                                    // rigid2d.cpp:163-164
+      const double wy = st * px + ct * py + ty;
+      int gi, gj;
+      if (pf_world2grid(c, wx, wy, gi, gj)) {
+        e = ((uint32_t)gi << 16) | (uint32_t)gj;
+        if (want_pz) {
+          const uint32_t d2 = d2_plane[gi * c.xsize + gj];
+          const int t = (int)min(d2, (uint32_t)(c.pz_n - 1));
+          pz[b] = t < c.pz_stage ? s_pz[t] : __ldg(&c.pz_table[t]);
+        }
+      } else {
+        ok = false;
+        e = 0xFFFFFFFEu;   // valid beam, off the map
+      }
+    }
+    ep[b] = e;
+  }
+  __syncwarp();
+  return __all_sync(kFullMask, ok);
+}
+
+// p = 1; for every valid beam in order: p *= pz (grid_mapper.cpp:88-128).  Redundant on all lanes.
+__device__ __forceinline__ double pf_ordered_product(const uint32_t *ep, const double *pz, int n)
+{
+  double p = 1.0;
+  for (int b = 0; b < n; b++)
+    if (ep[b] < 0xFFFFFFFEu) p *= pz[b];
+  return p;
+}
+
+// ---- integrateScan without the distance field (grid_mapper.cpp:140-178, 438-546, 549-807) -------------------------
+__device__ __forceinline__ void pf_integrate_rays(const PfConst &c, const uint32_t *ep, int n, int i0, int j0, double *L,
+                                                  OccSetDev &occ, int lane)
+{
+  const int xs = c.xsize;
+  for (int b = 0; b < n; b++) {
+    const uint32_t e = ep[b];
+    if (e >= 0xFFFFFFFEu) continue;
+    const int i1 = (int)(e >> 16), j1 = (int)(e & 0xFFFFu);
+    const int dx = i1 - i0, dy = j1 - j0;
+    const int adx = abs(dx), ady = abs(dy);
+    // the k-th free cell of freeGridIndex, by direction class
+    int len, kind;          // kind 0: axis / diagonal walk from the robot cell; 1: lineLow; 2: lineHigh
+    int sx = 0, sy = 0;     // step of kind 0
+    int ax = 0, ay = 0, inc = 1, dmaj = 1, dmin = 0;
+    if (dx == 0) { kind = 0; len = ady; sy = dy < 0 ? -1 : 1; }
+    else if (dy == 0) { kind = 0; len = adx; sx = dx < 0 ? -1 : 1; }
+    else if (ady < adx) {
+      // start cell pushed explicitly, then lineLow from the end with the smaller x (ctr == 0 skipped)
+      kind = 1; len = adx; dmaj = adx; dmin = ady;
+      if (i0 > i1) { ax = i1; ay = j1; inc = (j0 - j1) < 0 ? -1 : 1; }
+      else { ax = i0; ay = j0; inc = dy < 0 ? -1 : 1; }
+    } else if (ady > adx) {
+      kind = 2; len = ady; dmaj = ady; dmin = adx;
+      if (j0 > j1) { ax = i1; ay = j1; inc = (i0 - i1) < 0 ? -1 : 1; }
+      else { ax = i0; ay = j0; inc = dx < 0 ? -1 : 1; }
+    } else { kind = 0; len = adx; sx = dx < 0 ? -1 : 1; sy = dy < 0 ? -1 : 1; }
+
+    for (int base = 0; base < len; base += 32) {
+      const int k = base + lane;
+      const bool has = k < len;
+      uint32_t cell = 0;
+      bool erase = false;
+      if (has) {
+        int ci, cj;
+        if (kind == 0 || k == 0) { ci = i0 + sx * k; cj = j0 + sy * k; }
+        else {
+          // Bresenham error term in closed form: minor-axis increments before step k
+          const int a = 2 * dmin * k - dmaj;
+          const int nk = a > 0 ? (a + 2 * dmaj - 1) / (2 * dmaj) : 0;
+          if (kind == 1) { ci = ax + k; cj = ay + inc * nk; }
+          else { ci = ax + inc * nk; cj = ay + k; }
+        }
+        cell = (uint32_t)(ci * xs + cj);
+        const double lo = L[cell];
+        const double ln = lo + c.d_free;                      // grid_mapper.cpp:163
+        L[cell] = ln;
+        erase = (lo >= c.t_occ) && !(ln >= c.t_occ);          // occupied -> unknown band: leaves occ_cells_
+      }
+      unsigned m = __ballot_sync(kFullMask, erase);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        const uint32_t key = __shfl_sync(kFullMask, cell, src);
+        occ_erase(occ, key, lane);
+        m &= m - 1;
+      }
+    }
+    __syncwarp();
+    // the end-point cell (grid_mapper.cpp:172-176)
+    const uint32_t cell = (uint32_t)(i1 * xs + j1);
+    const double lo = L[cell];
+    const double ln = lo + c.d_occ;
+    __syncwarp();
+    if (lane == 0) L[cell] = ln;
+    if (!(lo >= c.t_occ) && (ln >= c.t_occ)) occ_insert(occ, cell, lane);
+    __syncwarp();
+  }
+}
+
+// shared-memory tables staged by TMA: beam cos/sin and the head of the likelihood table
+__device__ __forceinline__ void pf_stage_tables(const PfConst &c, int n_beams, double *s_beam, double *s_pz, uint64_t *bar)
+{
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t b0 = (uint32_t)n_beams * 16u, b1 = (uint32_t)c.pz_stage * 8u;
+    mbar_expect_tx(bar, b0 + b1);
+    tma_load_1d(s_beam, c.beam_cs, b0, bar);
+    tma_load_1d(s_pz, c.pz_table, b1, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// dynamic shared memory layout shared by the per-particle kernels:
+//   [bar 16 B][s_beam n*16][s_pz pz_stage*8][per warp: pz n*8, ep n*4]
+__host__ __device__ inline size_t pf_smem_bytes(int n_beams, int pz_stage, int warps)
+{
+  const size_t n = (size_t)((n_beams + 3) & ~3);
+  return 16 + n * 16 + (size_t)pz_stage * 8 + (size_t)warps * (n * 8 + n * 4);
+}
+
+// ---- SLAM, motion-model branch: sample, weight, integrate (particle_filter.cpp:158-176, 235-239) -------------------
+// mode 0: full step; mode 1: likelihood only at the current poses into out[] (tap, nothing is modified)
+__global__ void __launch_bounds__(kPfWarpsPerCta * 32) rbpf_update_kernel(const __grid_constant__ PfConst c, const PfPlanes pl,
+                                                                           const __grid_constant__ PfCall q, int mode, double *out)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n = q.n_beams;
+  const int npad = (n + 3) & ~3;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  double *s_beam = reinterpret_cast<double *>(smem + 16);
+  double *s_pz = s_beam + 2 * npad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w_pz = s_pz + c.pz_stage + (size_t)warp * npad;
+  uint32_t *w_ep = reinterpret_cast<uint32_t *>(s_pz + c.pz_stage + (size_t)kPfWarpsPerCta * npad) + (size_t)warp * npad;
+
+  pf_stage_tables(c, n, s_beam, s_pz, bar);
+
+  const int p = blockIdx.x * kPfWarpsPerCta + warp;
+  if (p >= c.N) return;
+  PfParticle *me = pl.meta + p;
+  double th = me->pose[0], x = me->pose[1], y = me->pose[2];
+  const uint32_t n_occ = me->n_occ;
+  const uint32_t *d2_plane = pl.d2 + (size_t)p * c.gstride;
+
+  if (mode == 0) {
+    // sampleMotionModel (particle_filter.cpp:295-322); L * z for the diagonal motion noise is sig[i] * z[i]
+    const int gid = q.particle_offset + p;
+    const double w0 = c.sig[0] * pf_std_normal(q, p, gid, 0);
+    const double w1 = c.sig[1] * pf_std_normal(q, p, gid, 1);
+    const double w2 = c.sig[2] * pf_std_normal(q, p, gid, 2);
+    if (lane == 0) { me->prev_pose[0] = th; me->prev_pose[1] = x; me->prev_pose[2] = y; }
+    if (pf_almost_zero(q.u_w)) {
+      th = pf_normalize_angle_pi(th + w0);
+      x += q.u_vx * cos(th) + w1;
+      y += q.u_vx * sin(th) + w2;
+    } else {
+      th = pf_normalize_angle_pi(th + q.u_w + w0);
+      x += (-q.u_vx / q.u_w) * sin(th) + (q.u_vx / q.u_w) * sin(th + q.u_w) + w1;
+      y += (q.u_vx / q.u_w) * cos(th) - (q.u_vx / q.u_w) * cos(th + q.u_w) + w2;
+    }
+  }
+
+  const bool on_map = pf_end_points(c, q.scan, n, s_beam, s_pz, d2_plane, th, x, y, w_ep, w_pz, n_occ > 0, lane);
+  // likelihoodFieldModel returns 1.0 before looking at any end point when the map has no obstacle (grid_mapper.cpp:94-98)
+  double lik = 1.0;
+  if (n_occ > 0) {
+    if (!on_map) { if (lane == 0) atomicOr(q.status, kPfStatusOffMap); return; }
+    lik = pf_ordered_product(w_ep, w_pz, n);
+  }
+  if (mode == 1) { if (lane == 0) out[p] = lik; return; }
+
+  int i0, j0;
+  const bool pose_on_map = pf_world2grid(c, x, y, i0, j0);
+  if (!on_map || !pose_on_map) { if (lane == 0) atomicOr(q.status, kPfStatusOffMap); return; }
+
+  OccSetDev occ;
+  occ.nxt = pl.nxt + (size_t)p * c.nxt_stride; occ.bkt = pl.bkt + (size_t)p * c.bkt_stride;
+  occ.G = (uint32_t)c.G; occ.bucket_count = me->bucket_count; occ.count = n_occ; occ.next_resize = me->next_resize;
+  occ.chain = me->chain;
+  pf_integrate_rays(c, w_ep, n, i0, j0, pl.log_odds + (size_t)p * c.gstride, occ, lane);
+
+  if (lane == 0) {
+    me->pose[0] = th; me->pose[1] = x; me->pose[2] = y;
+    me->weight = me->weight * lik;                         // particle_filter.cpp:175
+    me->n_occ = occ.count; me->bucket_count = occ.bucket_count; me->next_resize = occ.next_resize; me->chain = occ.chain;
+  }
+}
+
+// ---- improved proposal (particle_filter.cpp:178-233, 504-599, 383-437) followed by the same map integration ------
+__device__ __forceinline__ bool pf_pdf_normal(double a, double b, double &out)
+{
+  const double PI = 3.14159265358979323846;
+  if (pf_almost_zero(b)) return false;                      // grid_mapper.cpp:20-23 throws
+  const double sqrt_inv = 1.0 / sqrt(2.0 * PI * b);
+  const double var = -0.5 * (a * a) / b;
+  out = sqrt_inv * exp(var);
+  return true;
+}
+
+__device__ __forceinline__ bool pf_pose_likelihood_odom(const PfConst &c, const double *cur, const double *prev, const double *co,
+                                                        const double *po, double &out)
+{
+  const double rot1 = atan2(co[2] - po[2], co[1] - po[1]) - po[0];
+  const double trans = sqrt((co[1] - po[1]) * (co[1] - po[1]) + (co[2] - po[2]) * (co[2] - po[2]));
+  const double rot2 = pf_normalize_angle_pi(pf_normalize_angle_pi(co[0]) - pf_normalize_angle_pi(po[0]) - rot1);
+  const double rot1_hat = atan2(cur[2] - prev[2], cur[1] - prev[1]) - prev[0];
+  const double trans_hat = sqrt((cur[1] - prev[1]) * (cur[1] - prev[1]) + (cur[2] - prev[2]) * (cur[2] - prev[2]));
+  const double rot2_hat = pf_normalize_angle_pi(pf_normalize_angle_pi(cur[0]) - pf_normalize_angle_pi(prev[0]) - rot1_hat);
+  const double temp1 = c.srr * rot1_hat * rot1_hat + c.srt * trans_hat * trans_hat;
+  const double temp2 = c.str * trans_hat * trans_hat + c.stt * rot1_hat * rot1_hat + c.stt * rot2_hat * rot2_hat;
+  const double temp3 = c.srr * rot2_hat * rot2_hat + c.srt * trans_hat * trans_hat;
+  double p1, p2, p3;
+  if (!pf_pdf_normal(pf_normalize_angle_pi(pf_normalize_angle_pi(rot1) - pf_normalize_angle_pi(rot1_hat)), temp1, p1)) return false;
+  if (!pf_pdf_normal(trans - trans_hat, temp2, p2)) return false;
+  if (!pf_pdf_normal(pf_normalize_angle_pi(pf_normalize_angle_pi(rot2) - pf_normalize_angle_pi(rot2_hat)), temp3, p3)) return false;
+  out = p1 * p2 * p3;
+  return true;
+}
+
+// Eigen LLT (unblocked Cholesky, stops at the first non-positive pivot) then mu + L * z
+__device__ __forceinline__ void pf_sample_gaussian3(const double mu[3], double a[3][3], const double z[3], double out[3])
+{
+  for (int k = 0; k < 3; k++) {
+    double x = a[k][k];
+    for (int r = 0; r < k; r++) x -= a[k][r] * a[k][r];
+    if (x <= 0.0) break;
+    x = sqrt(x);
+    a[k][k] = x;
+    for (int i = k + 1; i < 3; i++) {
+      double s = 0.0;
+      for (int r = 0; r < k; r++) s += a[i][r] * a[k][r];
+      a[i][k] = (a[i][k] - s) / x;
+    }
+  }
+  for (int i = 0; i < 3; i++) {
+    const double l0 = a[i][0], l1 = i >= 1 ? a[i][1] : 0.0, l2 = i >= 2 ? a[i][2] : 0.0;
+    out[i] = mu[i] + ((l0 * z[0] + l1 * z[1]) + l2 * z[2]);
+  }
+}
+
+__global__ void __launch_bounds__(kPfWarpsPerCta * 32) rbpf_proposal_kernel(const __grid_constant__ PfConst c, const PfPlanes pl,
+                                                                             const __grid_constant__ PfCall q, double *samples)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n = q.n_beams;
+  const int npad = (n + 3) & ~3;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  double *s_beam = reinterpret_cast<double *>(smem + 16);
+  double *s_pz = s_beam + 2 * npad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w_pz = s_pz + c.pz_stage + (size_t)warp * npad;
+  uint32_t *w_ep = reinterpret_cast<uint32_t *>(s_pz + c.pz_stage + (size_t)kPfWarpsPerCta * npad) + (size_t)warp * npad;
+
+  pf_stage_tables(c, n, s_beam, s_pz, bar);
+
+  const int p = blockIdx.x * kPfWarpsPerCta + warp;
+  if (p >= c.N) return;
+  PfParticle *me = pl.meta + p;
+  const int gid = q.particle_offset + p;
+  const double pose[3] = {me->pose[0], me->pose[1], me->pose[2]};
+  const double prev[3] = {me->prev_pose[0], me->prev_pose[1], me->prev_pose[2]};
+  const uint32_t n_occ = me->n_occ;
+  const uint32_t *d2_plane = pl.d2 + (size_t)p * c.gstride;
+  double *my_samples = samples + (size_t)p * c.k_samples * 4;     // x[3], likelihood
+
+  // T_x = T(pose) * Ticp (particle_filter.cpp:181-183, rigid2d.cpp:221-231)
+  double sp, cp;
+  sincos(pose[0], &sp, &cp);
+  const double mx = cp * q.icp[1] - sp * q.icp[2] + pose[1];
+  const double my = sp * q.icp[1] + cp * q.icp[2] + pose[2];
+  const double mth = pose[0] + q.icp[0];
+
+  // sampleMode + gaussianProposal first pass
+  double mu[3] = {0.0, 0.0, 0.0}, eta = 0.0;
+  bool bad_map = false, bad_num = false;
+  for (int s = 0; s < c.k_samples; s++) {
+    double xj[3];
+    xj[0] = pf_normalize_angle_pi(mth + c.sig_mode[0] * pf_std_normal(q, p, gid, 3 * s + 0));
+    xj[1] = mx + c.sig_mode[1] * pf_std_normal(q, p, gid, 3 * s + 1);
+    xj[2] = my + c.sig_mode[2] * pf_std_normal(q, p, gid, 3 * s + 2);
+    const bool on_map = pf_end_points(c, q.scan, n, s_beam, s_pz, d2_plane, xj[0], xj[1], xj[2], w_ep, w_pz, n_occ > 0, lane);
+    double p_scan = 1.0;
+    if (n_occ > 0) {
+      if (!on_map) { bad_map = true; break; }
+      p_scan = pf_ordered_product(w_ep, w_pz, n);
+    }
+    __syncwarp();
+    double p_pose;
+    if (!pf_pose_likelihood_odom(c, xj, prev, q.cur_od, q.prev_od, p_pose)) { bad_num = true; break; }
+    p_scan = fmin(fmax(p_scan, c.scan_min), c.scan_max);           // std::clamp, :548-549
+    p_pose = fmin(fmax(p_pose, c.pose_min), c.pose_max);
+    const double lik = p_scan * p_pose;
+    if (lane == 0) { my_samples[4 * s + 0] = xj[0]; my_samples[4 * s + 1] = xj[1]; my_samples[4 * s + 2] = xj[2]; my_samples[4 * s + 3] = lik; }
+    for (int i = 0; i < 3; i++) mu[i] += xj[i] * lik;
+    eta += lik;
+  }
+  if (!bad_map && !bad_num && pf_almost_zero(eta)) bad_num = true;      // "eta is 0", :577-580
+  if (bad_map || bad_num) { if (lane == 0) atomicOr(q.status, bad_map ? kPfStatusOffMap : kPfStatusNumeric); return; }
+  __syncwarp();
+  for (int i = 0; i < 3; i++) mu[i] /= eta;
+  mu[0] = pf_normalize_angle_pi(mu[0]);
+  double sigma[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int s = 0; s < c.k_samples; s++) {
+    const double d[3] = {my_samples[4 * s + 0] - mu[0], my_samples[4 * s + 1] - mu[1], my_samples[4 * s + 2] - mu[2]};
+    const double lik = my_samples[4 * s + 3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) sigma[a][b] += (d[a] * d[b]) * lik;
+  }
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) sigma[a][b] /= eta;
+  const int d0 = 3 * c.k_samples;
+  const double z[3] = {pf_std_normal(q, p, gid, d0), pf_std_normal(q, p, gid, d0 + 1), pf_std_normal(q, p, gid, d0 + 2)};
+  double np[3];
+  pf_sample_gaussian3(mu, sigma, z, np);                               // :214
+
+  // integrateScan at the new pose (:235-239)
+  const bool on_map = pf_end_points(c, q.scan, n, s_beam, s_pz, d2_plane, np[0], np[1], np[2], w_ep, w_pz, false, lane);
+  int i0, j0;
+  const bool pose_on_map = pf_world2grid(c, np[1], np[2], i0, j0);
+  if (!on_map || !pose_on_map) { if (lane == 0) atomicOr(q.status, kPfStatusOffMap); return; }
+  OccSetDev occ;
+  occ.nxt = pl.nxt + (size_t)p * c.nxt_stride; occ.bkt = pl.bkt + (size_t)p * c.bkt_stride;
+  occ.G = (uint32_t)c.G; occ.bucket_count = me->bucket_count; occ.count = n_occ; occ.next_resize = me->next_resize;
+  occ.chain = me->chain;
+  pf_integrate_rays(c, w_ep, n, i0, j0, pl.log_odds + (size_t)p * c.gstride, occ, lane);
+  if (lane == 0) {
+    for (int i = 0; i < 3; i++) { me->prev_pose[i] = pose[i]; me->pose[i] = np[i]; }
+    me->weight = me->weight * eta;                                      // :231
+    me->n_occ = occ.count; me->bucket_count = occ.bucket_count; me->next_resize = occ.next_resize; me->chain = occ.chain;
+  }
+}
+
+// ---- distance field: the reference's brushfire (grid_mapper.cpp:272-435) ---------------------------------------------
+// One warp (= one CTA) per particle in flight.  Heap entry = d2 << 32 | source cell << 16 | cell; the comparator of
+// grid_mapper.hpp:104-111 (a.occ_dist > b.occ_dist) is the comparison of d2.  Entry i lives in slot i + 1 so
+// that the two children of a node share one 16-byte shared-memory word pair; entries beyond `hcap` spill to a
+// per-CTA global scratch.
+struct HeapDev
+{
+  unsigned long long *s;   // shared, hcap + 2 slots
+  unsigned long long *g;   // global spill
+  int hcap, len;
+  __device__ __forceinline__ unsigned long long get(int i) const { return i < hcap ? s[i + 1] : g[i - hcap]; }
+  __device__ __forceinline__ void set(int i, unsigned long long v) { if (i < hcap) s[i + 1] = v; else g[i - hcap] = v; }
+  // std::__push_heap(first, hole, top = 0, value)
+  __device__ __forceinline__ void sift_up(int hole, unsigned long long value)
+  {
+    const uint32_t vk = (uint32_t)(value >> 32);
+    while (hole > 0) {
+      const int parent = (hole - 1) >> 1;
+      const unsigned long long pe = get(parent);
+      if ((uint32_t)(pe >> 32) > vk) { set(hole, pe); hole = parent; }
+      else break;
+    }
+    set(hole, value);
+  }
+  __device__ __forceinline__ void push(unsigned long long e) { sift_up(len, e); len++; }
+  // std::pop_heap + pop_back: __adjust_heap(first, 0, len - 1, last value)
+  __device__ __forceinline__ void pop()
+  {
+    if (len > 1) {
+      const int L = len - 1;
+      const unsigned long long value = get(L);
+      int hole = 0, second = 0;
+      while (second < (L - 1) / 2) {
+        second = 2 * (second + 1);
+        unsigned long long r, l;
+        if (second < hcap) {
+          const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(&s[second]);   // slots second, second + 1 = entries second - 1, second
+          l = pr.x; r = pr.y;
+        } else { r = get(second); l = get(second - 1); }
+        unsigned long long mv = r;
+        if ((uint32_t)(r >> 32) > (uint32_t)(l >> 32)) { second--; mv = l; }
+        set(hole, mv);
+        hole = second;
+      }
+      if ((L & 1) == 0 && second == (L - 2) / 2) {
+        second = 2 * (second + 1);
+        set(hole, get(second - 1));
+        hole = second - 1;
+      }
+      sift_up(hole, value);
+    }
+    len--;
+  }
+};
+
+__host__ __device__ inline size_t pf_esdf_smem_bytes(int G, int hcap) { return (size_t)(hcap + 2) * 8 + (size_t)((G + 31) / 32) * 4; }
+
+__global__ void __launch_bounds__(32) rbpf_distance_field_kernel(const __grid_constant__ PfConst c, const PfPlanes pl, int hcap,
+                                                                  unsigned long long *spill, unsigned long long *stats)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x;
+  HeapDev H;
+  H.s = reinterpret_cast<unsigned long long *>(smem);
+  H.g = spill + (size_t)blockIdx.x * c.G;
+  H.hcap = hcap;
+  uint32_t *marked = reinterpret_cast<uint32_t *>(smem + (size_t)(hcap + 2) * 8);
+  const int words = (c.G + 31) / 32;
+  const int xs = c.xsize, ys = c.ysize, R = c.cell_radius;
+  unsigned long long iters = 0, heap_max = 0;
+
+  for (int p = blockIdx.x; p < c.N; p += gridDim.x) {
+    const PfParticle *me = pl.meta + p;
+    if (me->n_occ == 0) continue;                                        // grid_mapper.cpp:335-338
+    const uint16_t *nxt = pl.nxt + (size_t)p * c.nxt_stride;
+    uint32_t *d2p = pl.d2 + (size_t)p * c.gstride;
+    for (int w = lane; w < words; w += 32) marked[w] = 0;
+    __syncwarp();
+    H.len = 0;
+    // seeds in the iteration order of occ_cells_ (:348-361); all of distance 0, so push_heap leaves them in place
+    for (uint32_t key = nxt[c.G]; key != kNil16; key = nxt[key]) {
+      if (lane == 0) { d2p[key] = 0; marked[key >> 5] |= 1u << (key & 31); }
+      H.push(((unsigned long long)key << 16) | key);
+    }
+    __syncwarp();
+    while (H.len > 0) {
+      const unsigned long long top = H.get(0);                          // Q.top(), :399
+      const int cell = (int)(top & 0xFFFFu), src = (int)((top >> 16) & 0xFFFFu);
+      const int ci = cell / xs, cj = cell - ci * xs, si = src / xs, sj = src - si * xs;
+      // lanes 0..3: (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
+      bool valid = false;
+      unsigned long long entry = 0;
+      if (lane < 4) {
+        const int ni = ci + (lane == 0 ? -1 : lane == 2 ? 1 : 0), nj = cj + (lane == 1 ? -1 : lane == 3 ? 1 : 0);
+        const bool inb = lane == 0 ? ci > 0 : lane == 1 ? cj > 0 : lane == 2 ? ci < xs - 1 : cj < ys - 1;
+        if (inb) {
+          const int idx = ni * xs + nj;                                  // grid2RowMajor
+          if (!((marked[idx >> 5] >> (idx & 31)) & 1u)) {
+            const int di = abs(ni - si), dj = abs(nj - sj);
+            const int d2 = di * di + dj * dj;
+            if (di < R && dj < R && d2 <= R * R) {                       // distances_.at() range, dist > cell_radius_
+              valid = true;
+              d2p[idx] = (uint32_t)d2;
+              atomicOr(&marked[idx >> 5], 1u << (idx & 31));
+              entry = ((unsigned long long)(uint32_t)d2 << 32) | ((unsigned long long)src << 16) | (unsigned long long)idx;
+            }
+          }
+        }
+      }
+      unsigned m = __ballot_sync(kFullMask, valid);
+      while (m) {
+        const int from = __ffs(m) - 1;
+        H.push(__shfl_sync(kFullMask, entry, from));
+        m &= m - 1;
+      }
+      if ((unsigned long long)H.len > heap_max) heap_max = H.len;
+      H.pop();                                                           // pops whatever is on top NOW, :431
+      iters++;
+      __syncwarp();
+    }
+  }
+  if (stats && lane == 0) { atomicAdd(&stats[0], iters); atomicMax(&stats[1], heap_max); }
+}
+
+// ---- normalise, N_eff, low-variance walk (particle_filter.cpp:442-500) -----------------------------------------------
+struct PfResample
+{
+  double *w;            // [n_total] gathered weights in global particle order, normalised in place
+  int32_t *ancestors;   // [n_total]
+  int *info;            // [0] = N_eff as printed, [1] = resampled
+};
+
+// one warp; every lane runs the same sequential fp64 chain on values fetched 32 at a time
+__global__ void __launch_bounds__(32) rbpf_normalize_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
+{
+  const int lane = threadIdx.x;
+  double sum = 0.0;
+  for (int base = 0; base < n_total; base += 32) {
+    const double v = base + lane < n_total ? r.w[base + lane] : 0.0;
+    const int cnt = min(32, n_total - base);
+    for (int i = 0; i < cnt; i++) sum += __shfl_sync(kFullMask, v, i);
+  }
+  double sq = 0.0;
+  for (int base = 0; base < n_total; base += 32) {
+    double v = 0.0;
+    if (base + lane < n_total) { v = r.w[base + lane] / sum; r.w[base + lane] = v; }
+    const int cnt = min(32, n_total - base);
+    for (int i = 0; i < cnt; i++) { const double wi = __shfl_sync(kFullMask, v, i); sq += wi * wi; }   // std::pow(w, 2)
+  }
+  __syncwarp();
+  const int neff = (int)(1.0 / sq);                                        // :463-464
+  const bool resample = neff < (n_total / 2);
+  if (lane == 0) { r.info[0] = neff; r.info[1] = resample ? 1 : 0; }
+  if (!resample) {
+    for (int m = lane; m < n_total; m += 32) r.ancestors[m] = m;
+    return;
+  }
+  if (lane == 0) {
+    double z;
+    if (q.ext) z = q.ext[(size_t)q.ext_per];                               // caller passes a pointer to the last variate
+    else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
+    const double rr = z / (double)n_total;                                 // :475-476
+    double cacc = r.w[0];
+    int i = 0;
+    const double step = 1.0 / (n_total - 1);
+    for (int m = 0; m < n_total; m++) {
+      const double U = rr + (double)(m * step);                            // :485
+      while (U > cacc) {
+        i++;
+        if (i > n_total - 1) { i = n_total - 1; break; }
+        cacc += r.w[i];
+      }
+      r.ancestors[m] = i;
+    }
+  }
+}
+
+__global__ void rbpf_gather_weights_kernel(const PfParticle *meta, double *w, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = meta[i].weight;
+}
+
+// after normalisation every particle's weight is the normalised one (resampled or not)
+__global__ void rbpf_scatter_weights_kernel(PfParticle *meta, const double *w, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) meta[i].weight = w[i];
+}
+
+// particle m of dst <- particle ancestors[m] of src, plane by plane with 16-byte accesses; blockIdx.y = m
+__global__ void __launch_bounds__(256) rbpf_copy_particles_kernel(const __grid_constant__ PfConst c, const PfPlanes src, const PfPlanes dst,
+                                                                   const int32_t *ancestors, int anc_offset)
+{
+  const int m = blockIdx.y;
+  const int a = ancestors[anc_offset + m] - anc_offset;      // local source index (host guarantees it is local)
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const uint4 *s0 = reinterpret_cast<const uint4 *>(src.log_odds + (size_t)a * c.gstride);
+  uint4 *d0 = reinterpret_cast<uint4 *>(dst.log_odds + (size_t)m * c.gstride);
+  for (int i = tid; i < c.gstride / 2; i += nth) d0[i] = s0[i];
+  const uint4 *s1 = reinterpret_cast<const uint4 *>(src.d2 + (size_t)a * c.gstride);
+  uint4 *d1 = reinterpret_cast<uint4 *>(dst.d2 + (size_t)m * c.gstride);
+  for (int i = tid; i < c.gstride / 4; i += nth) d1[i] = s1[i];
+  const uint4 *s2 = reinterpret_cast<const uint4 *>(src.nxt + (size_t)a * c.nxt_stride);
+  uint4 *d2 = reinterpret_cast<uint4 *>(dst.nxt + (size_t)m * c.nxt_stride);
+  for (int i = tid; i < c.nxt_stride / 8; i += nth) d2[i] = s2[i];
+  const int used = (int)((src.meta[a].bucket_count + 7) / 8);
+  const uint4 *s3 = reinterpret_cast<const uint4 *>(src.bkt + (size_t)a * c.bkt_stride);
+  uint4 *d3 = reinterpret_cast<uint4 *>(dst.bkt + (size_t)m * c.bkt_stride);
+  for (int i = tid; i < used; i += nth) d3[i] = s3[i];
+  if (tid == 0) dst.meta[m] = src.meta[a];
+}
+
+// ---- getRobotState / newMap (particle_filter.cpp:255-291, grid_mapper.cpp:185-226) ----------------------------------
+// first particle with the largest weight, strict > starting from 0.0 (so index 0 when nothing is positive)
+__global__ void __launch_bounds__(1024) rbpf_best_kernel(const PfParticle *meta, int n, int *best, double *best_pose_weight)
+{
+  __shared__ double sw[32];
+  __shared__ int si[32];
+  double bw = 0.0;
+  int bi = 0x7FFFFFFF;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double w = meta[i].weight;
+    if (w > bw) { bw = w; bi = i; }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ow = __shfl_xor_sync(kFullMask, bw, d);
+    const int oi = __shfl_xor_sync(kFullMask, bi, d);
+    if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sw[threadIdx.x >> 5] = bw; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bw = threadIdx.x < (blockDim.x >> 5) ? sw[threadIdx.x] : 0.0;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7FFFFFFF;
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ow = __shfl_xor_sync(kFullMask, bw, d);
+      const int oi = __shfl_xor_sync(kFullMask, bi, d);
+      if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      const int b = (bi == 0x7FFFFFFF) ? 0 : bi;
+      *best = b;
+      best_pose_weight[0] = meta[b].pose[0]; best_pose_weight[1] = meta[b].pose[1]; best_pose_weight[2] = meta[b].pose[2];
+      best_pose_weight[3] = bw;
+    }
+  }
+}
+
+// occupancy export of one particle: prob from the log-odds exactly as updateCellState left it, transposed output
+__global__ void rbpf_export_map_kernel(const __grid_constant__ PfConst c, const double *log_odds, const int *which, int8_t *out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.G) return;
+  const double l = log_odds[(size_t)(*which) * c.gstride + i];
+  const int row = i / c.xsize, col = i - row * c.xsize;
+  const int idx = col * c.xsize + row;                                      // grid_mapper.cpp:195-197
+  int8_t v;
+  if (l >= c.t_occ) v = 100;                                                // prob := 1
+  else if (l <= c.t_free) v = 0;                                            // prob := 0
+  else {
+    const double prob = 1 - (1 / (1 + exp(l)));                             // grid_mapper.hpp:27-30
+    v = (prob == 0.5) ? (int8_t)-1 : (int8_t)(prob * 100);
+  }
+  out[idx] = v;
+}
+
+} // namespace b2n

@@ -1,0 +1,33 @@
+"""Quick timing probe of the RBPF path on one GPU (not the bench): per-kernel CUDA-event times at a given size."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _pkg  # noqa: E402
+import _oracle as orc  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+scans = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+hcap = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
+pkg = _pkg.load()
+poses, twists = orc.circle_path(scans)
+rng = np.random.default_rng(4)
+f = pkg.bmapping.make_filter(orc.pf_params(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3)))
+f.setHeapCapacity(hcap)
+f.seed(1)
+f.setKernelTiming(True)
+for i in range(scans):
+    scan = orc.room_scan(poses[i + 1], rng=rng)
+    t0 = time.perf_counter()
+    f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = f.kernelTimes()
+    neff, rs, _ = f.resampleInfo()
+    print("scan %d: wall %.2f ms | update %.3f ms, distance field %.3f ms, normalise+resample %.3f ms | N_eff %d resampled %d | %.0f particle-updates/s"
+          % (i, wall, ms[0], ms[1], ms[2], neff, rs, N / (wall * 1e-3)))
+print("distance-field stats (iterations, heap max):", f.distanceFieldStats())
