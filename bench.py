@@ -129,6 +129,99 @@ def cpu_oracle_port(budget_s=10.0):
     }
 
 
+# ------------------------------------------------------------------------------ RBPF leg --------
+RBPF_N, RBPF_BEAMS, RBPF_CELLS = 4096, 360, 200 * 200      # BASELINE configs[2]
+RBPF_MOTION_NOISE = (2e-3, 1e-3, 1e-3)                      # raised so that weights diverge and resampling fires
+# per particle-update, distance field = read 8 B occupancy + write 4 B distance per cell
+RBPF_DF_BYTES_PER_PARTICLE = 12 * RBPF_CELLS
+
+
+def rbpf_inputs(n_scans, seed=4):
+    import numpy as np
+    import _oracle as orc
+    poses, twists = orc.circle_path(n_scans)
+    rng = np.random.default_rng(seed)
+    scans = [orc.room_scan(poses[i + 1], rng=rng) for i in range(n_scans)]
+    return poses, twists, scans
+
+
+def rbpf_cpu(kind, budget_s=12.0, n_particles=64):
+    """bmapping::ParticleFilter::SLAM() on the host, one thread: the compiled reference (kind 'reference') or the
+    oracle port, on `n_particles` of the 4096 particles (its cost is linear in the particle count)."""
+    import _oracle as orc
+    poses, twists, scans = rbpf_inputs(40)
+    q = dict(num_particles=n_particles, init_pose=tuple(poses[0]), motion_noise=RBPF_MOTION_NOISE)
+    if kind == "reference":
+        f = orc.RefPf(**q)
+        f.seed(1)
+    else:
+        f = orc.OraclePf(**q)
+        f.noise_mt19937(1)
+    done, t0 = 0, time.perf_counter()
+    for i in range(len(scans)):
+        f.slam(scans[i], twists[i], poses[i + 1], poses[i])
+        done += 1
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    return {"value": done * n_particles / el, "unit": "particle-updates/s", "cores": 1, "kind": kind,
+            "sample": "%d SLAM() calls on %d of the %d particles (360 beams, 200x200 map) in %.1f s; cost is linear in the particle count"
+                      % (done, n_particles, RBPF_N, el)}
+
+
+def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
+    """BASELINE configs[2]: RBPF 4096 particles, 360-beam synthetic lidar, 200x200 map, motion-model branch:
+    sample + beam weighting + ray integration + distance field + normalise + resample, every scan."""
+    poses, twists, scans = rbpf_inputs(n_scans + warmup)
+    f = pkg.bmapping.make_filter(__import__("_oracle").pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]),
+                                                                 motion_noise=RBPF_MOTION_NOISE))
+    f.seed(1)
+    f.setKernelTiming(True)
+    ms = [0.0, 0.0, 0.0]
+    resampled, wall = 0, 0.0
+    n0 = f.launchCount()
+    for i in range(n_scans + warmup):
+        if i == warmup:
+            n0 = f.launchCount()
+        t0 = time.perf_counter()
+        f.SLAM(scans[i], pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
+        dt_wall = time.perf_counter() - t0
+        if i >= warmup:
+            wall += dt_wall
+            k = f.kernelTimes()
+            for j in range(3):
+                ms[j] += k[j]
+            resampled += f.resampleInfo()[1]
+    launches = f.launchCount() - n0
+    dev_ms = sum(ms)
+    df_ms = ms[1] / n_scans
+    achieved = RBPF_N * RBPF_DF_BYTES_PER_PARTICLE / (df_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    out = {
+        "metric": "rbpf_particle_updates_per_sec", "unit": "particle-updates/s",
+        "value": RBPF_N * n_scans / (dev_ms * 1e-3),
+        "config": {"workload": "RBPF 4096 particles, 360-beam synthetic lidar, 200x200 occupancy grid (BASELINE configs[2]), motion-model branch",
+                   "particles": RBPF_N, "beams": RBPF_BEAMS, "cells": RBPF_CELLS, "scans": n_scans, "warmup_scans": warmup,
+                   "resampled_scans": int(resampled),
+                   "l2": "per-particle planes total %.1f GB >> 126 MB L2" % (RBPF_N * RBPF_CELLS * 12 / 1e9)},
+        "ms_per_scan": dev_ms / n_scans,
+        "kernel_ms_per_scan": {"update(sample+weight+rays)": ms[0] / n_scans, "distance_field": df_ms,
+                               "normalise+resample+copy": ms[2] / n_scans},
+        "e2e": {"value": RBPF_N * n_scans / wall, "unit": "particle-updates/s", "ms_per_scan": 1e3 * wall / n_scans,
+                "h2d_bytes_per_step": 4 * RBPF_BEAMS + 72, "d2h_bytes_per_step": 16,
+                "note": "synchronous SLAM(): host scan + twist + odometry in, status / N_eff / resample flag out"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "rbpf_distance_field_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel_ms": df_ms,
+                     "algorithmic_bytes_per_launch": RBPF_N * RBPF_DF_BYTES_PER_PARTICLE,
+                     "note": "the reference's brushfire is order-dependent (heap ties, seed order): serial per particle by definition, "
+                             "parallel over particles only - latency bound, not HBM bound (DESIGN.md 4.3)"},
+    }
+    f.close()
+    return out
+
+
 def run_reference_arm(args):
     """--impl reference: the unmodified reference controller::MPPI (oracle/_ref), single thread."""
     rank = int(os.environ.get("RANK", "0"))
@@ -174,6 +267,8 @@ def run_reference_arm(args):
         "note": "oracle/_ref = unmodified reference sources compiled with a mini-Eigen stand-in (Eigen is not installed); "
                 "single thread because the reference draws from one process-global mt19937_64",
     }
+    if not args.no_rbpf:
+        line["rbpf"] = rbpf_cpu(kind)
     print(json.dumps(line), flush=True)
 
 
@@ -302,6 +397,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_oracle_port()
+        if world == 1 and not args.no_rbpf:
+            line["rbpf"] = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3)
+            if not args.no_cpu:
+                line["rbpf"]["cpu_baseline"] = rbpf_cpu("port")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -315,6 +414,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-rbpf", action="store_true", help="skip the RBPF leg (BASELINE configs[2])")
+    ap.add_argument("--rbpf-scans", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 2000:
