@@ -126,10 +126,11 @@ void newControls(Mppi &m, double px, double py, double ptheta, double *ul, doubl
         duk[2 * i] = m.mt.normal(0.0, ul_sig);
         duk[2 * i + 1] = m.mt.normal(0.0, ur_sig);
       } else if (m.mode == 1) {
-        double z0, z1;
-        orc::philox_normal_pair(m.seed, orc::DOMAIN_MPPI, m.call, (uint32_t)(m.k_offset + k), (uint32_t)i, &z0, &z1);
-        duk[2 * i] = z0 * ul_sig;
-        duk[2 * i + 1] = z1 * ur_sig;
+        // one Philox call per PAIR of time steps: binary32 variates (L, R) of step 2j then of step 2j + 1
+        float z[4];
+        orc::philox_normal_quad_f32(m.seed, orc::DOMAIN_MPPI, m.call, (uint32_t)(m.k_offset + k), (uint32_t)(i >> 1), z);
+        duk[2 * i] = (double)z[2 * (i & 1)] * ul_sig;
+        duk[2 * i + 1] = (double)z[2 * (i & 1) + 1] * ur_sig;
       } else {
         duk[2 * i] = m.ext[((size_t)k * T + i) * 2];
         duk[2 * i + 1] = m.ext[((size_t)k * T + i) * 2 + 1];
@@ -277,6 +278,10 @@ void orc_mt_normals(uint64_t seed, int n, double mu, double sigma, double *out)
   for (int i = 0; i < n; i++) out[i] = s.normal(mu, sigma);
 }
 void orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc::philox4x32_10(ctr, key, out); }
+void orc_philox_normal_quad_f32(uint64_t seed, uint32_t domain, uint32_t call, uint32_t stream, uint32_t index, float *z)
+{
+  orc::philox_normal_quad_f32(seed, domain, call, stream, index, z);
+}
 void orc_philox_normal_pair(uint64_t seed, uint32_t domain, uint32_t call, uint32_t stream, uint32_t index, double *z)
 {
   orc::philox_normal_pair(seed, domain, call, stream, index, &z[0], &z[1]);

@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <random>
 
 namespace orc
@@ -118,6 +119,65 @@ inline void philox_normal_pair(uint64_t seed, uint32_t domain, uint32_t call, ui
   sincos_2pi(u2, &s, &c);
   *z0 = rad * c;
   *z1 = rad * s;
+}
+
+// ---- MPPI perturbations: binary32 Box-Muller built from correctly-rounded operations only --------------------
+// Restated independently of csrc/common.cuh::box_muller_f32.  Every step is one IEEE binary32 operation
+// (fmaf / sqrtf / + - * / on floats; this file is compiled with -ffp-contract=off) or exact integer work, so the
+// GPU and this code agree bit for bit.  One Philox call gives four variates: two consecutive time steps x (L, R).
+inline void box_muller_f32(uint32_t ra, uint32_t rb, float *z0, float *z1)
+{
+  const float a = (float)(ra >> 9) + 0.5f;                       // u1 = a * 2^-23 in (0,1)
+  int32_t ia;
+  std::memcpy(&ia, &a, 4);
+  int32_t ix = ia + (0x3f800000 - 0x3f3504f3);
+  const int e = (ix >> 23) - 127 - 23;
+  ix = (ix & 0x007fffff) + 0x3f3504f3;
+  float f;
+  std::memcpy(&f, &ix, 4);                                       // a = f * 2^(e+23), f in [sqrt(1/2), sqrt(2))
+  const float t = f - 1.0f;                                       // ln f = t P(t), degree-8 fit on [-0.293, 0.414]
+  float pl = std::fmaf(t, 0.0874394551f, -0.143773302f);
+  pl = std::fmaf(t, pl, 0.149490952f);
+  pl = std::fmaf(t, pl, -0.165606961f);
+  pl = std::fmaf(t, pl, 0.199569777f);
+  pl = std::fmaf(t, pl, -0.250021547f);
+  pl = std::fmaf(t, pl, 0.333341837f);
+  pl = std::fmaf(t, pl, -0.499999881f);
+  pl = std::fmaf(t, pl, 1.0f);
+  const float lnf = t * pl;
+  const float L = std::fmaf(-1.3862944f, (float)e, -2.0f * lnf); // -2 ln u1
+  const float rad = std::sqrt(L);
+  const int32_t sv = ((int32_t)(rb << 2)) >> 8;                  // 24 signed bits
+  const float y = ((float)sv + 0.5f) * 5.9604645e-08f;           // (-1/2, 1/2), never 0
+  const float ang = y * 1.5707964f;
+  const float z = ang * ang;
+  float ps = std::fmaf(z, -1.9515296e-4f, 8.3321609e-3f);
+  ps = std::fmaf(z, ps, -1.6666655e-1f);
+  ps = ps * z;
+  const float sn = std::fmaf(ang, ps, ang);
+  float pc = std::fmaf(z, 2.4433157e-5f, -1.3887316e-3f);
+  pc = std::fmaf(z, pc, 4.1666646e-2f);
+  pc = std::fmaf(z, pc, -0.5f);
+  const float cs = std::fmaf(z, pc, 1.0f);
+  float c, d;
+  switch (rb >> 30) {
+    case 0: c = cs; d = sn; break;
+    case 1: c = -sn; d = cs; break;
+    case 2: c = -cs; d = -sn; break;
+    default: c = sn; d = -cs; break;
+  }
+  *z0 = rad * c;
+  *z1 = rad * d;
+}
+
+inline void philox_normal_quad_f32(uint64_t seed, uint32_t domain, uint32_t call, uint32_t stream, uint32_t index, float z[4])
+{
+  const uint32_t ctr[4] = {index, stream, call, domain};
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t r[4];
+  philox4x32_10(ctr, key, r);
+  box_muller_f32(r[0], r[1], &z[0], &z[1]);
+  box_muller_f32(r[2], r[3], &z[2], &z[3]);
 }
 
 } // namespace orc

@@ -2,6 +2,8 @@
 // Host side of controller::MPPI (reference: controller/src/controller/mppi.cpp:28-69,72-140).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -15,7 +17,9 @@ using namespace b2n;
 struct b2n_mppi
 {
   b2n_mppi_params p;
-  int T = 0, K = 0, S = 1, device = 0;
+  int T = 0, K = 0, S = 4, G = 16, device = 0;
+  double plan_abs_max = 0.0;             // bound on |u| over the plan, the tail value and the clamp
+  bool force_generic = false;            // B2N_MPPI_GENERIC=1: never take the FAST rollout variant (tests)
   int n_sm = 0, grid = 0;
   size_t smem = 0;
   bool tma_store = false;
@@ -61,28 +65,69 @@ struct b2n_mppi
 namespace
 {
 
-template <int S>
-int launch_rollout_s(b2n_mppi *h, const MppiArgs &a)
+// (S, G) = steps per lane, lanes per rollout; G * S >= T.  The table below is every shape that is built.
+template <int S, int G>
+cudaError_t configure_shape(b2n_mppi *h)
 {
-  mppi_rollout_kernel<S><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);
-  return 0;
-}
-
-size_t rollout_smem(int S) { return (size_t)kMppiWarps * 2 * 32 * S * 3 * sizeof(float) + (size_t)32 * S * 6 * sizeof(double); }
-
-template <int S>
-cudaError_t configure_s(b2n_mppi *h)
-{
-  h->smem = rollout_smem(S);
-  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  h->smem = mppi_rollout_smem(S, G);
+  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S>, kMppiThreads, h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
+  int per_sm = 0, per_sm_fast = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false>, kMppiThreads, h->smem);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, mppi_rollout_kernel<S, G, true>, kMppiThreads, h->smem);
+  if (e != cudaSuccess) return e;
+  per_sm = std::max(per_sm, per_sm_fast);     // the partials buffer is sized for the larger grid; both variants stride by gridDim
   if (per_sm < 1) per_sm = 1;
-  const int want = (h->K + kMppiWarps - 1) / kMppiWarps;
+  // persistent grid: every SM filled to its residency limit (an evenly divided but smaller grid measured slower:
+  // SMs holding one CTA more than their neighbours set the pace)
+  const int per_cta = kMppiWarps * (32 / G);
+  const int want = (h->K + per_cta - 1) / per_cta;
   h->grid = std::max(1, std::min(want, per_sm * h->n_sm));
   return cudaSuccess;
+}
+
+#define B2N_MPPI_SHAPES(X) X(2, 8) X(4, 8) X(2, 16) X(4, 16) X(2, 32) X(4, 32) X(8, 32)
+
+cudaError_t configure(b2n_mppi *h)
+{
+#define X(S_, G_) if (h->S == S_ && h->G == G_) return configure_shape<S_, G_>(h);
+  B2N_MPPI_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+void launch_rollout(b2n_mppi *h, const MppiArgs &a, bool fast)
+{
+#define X(S_, G_)                                                                                          \
+  if (h->S == S_ && h->G == G_) {                                                                          \
+    if (fast) mppi_rollout_kernel<S_, G_, true><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);          \
+    else mppi_rollout_kernel<S_, G_, false><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);              \
+    return;                                                                                                \
+  }
+  B2N_MPPI_SHAPES(X)
+#undef X
+}
+
+// default shape: four steps per lane where the horizon allows it (fewest scan levels per step without running out
+// of registers); B2N_MPPI_SHAPE="S,G" overrides it for tuning runs
+void pick_shape(int T, int &S, int &G)
+{
+  if (T <= 16) { S = 2; G = 8; }
+  else if (T <= 32) { S = 4; G = 8; }
+  else if (T <= 64) { S = 4; G = 16; }
+  else if (T <= 128) { S = 4; G = 32; }
+  else { S = 8; G = 32; }
+  if (const char *env = std::getenv("B2N_MPPI_SHAPE")) {
+    int s = 0, g = 0;
+    if (std::sscanf(env, "%d,%d", &s, &g) == 2 && s * g >= T) {
+#define X(S_, G_) if (s == S_ && g == G_) { S = s; G = g; }
+      B2N_MPPI_SHAPES(X)
+#undef X
+    }
+  }
 }
 
 int set_device(const b2n_mppi *h)
@@ -96,13 +141,11 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   const b2n_mppi_params &p = h->p;
   MppiArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.r_half = p.wheel_radius / 2.0;
-  a.r_over_L = p.wheel_radius / p.wheel_base;
+  a.c_v = (p.wheel_radius / 2.0) * (p.dt / 6.0);
+  a.c_w = (p.wheel_radius / p.wheel_base) * p.dt;
   for (int i = 0; i < 3; i++) { a.Q[i] = p.Q[i]; a.P1[i] = p.P1[i]; a.xd[i] = h->xd[i]; }
   a.R[0] = p.R[0]; a.R[1] = p.R[1];
   a.inv_lambda = 1.0 / p.lambda;
-  a.h = p.dt;
-  a.h_sixth = p.dt / 6.0;
   a.sigL = std::sqrt(p.ul_var);       // mppi.cpp:176-177
   a.sigR = std::sqrt(p.ur_var);
   a.x0[0] = x; a.x0[1] = y; a.x0[2] = theta;   // mppi.cpp:75-76
@@ -128,12 +171,13 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
     h->ev_used += 2;
     B2N_CUDA(cudaEventRecord(e0, h->stream));
   }
-  switch (h->S) {
-    case 1: launch_rollout_s<1>(h, a); break;
-    case 2: launch_rollout_s<2>(h, a); break;
-    case 4: launch_rollout_s<4>(h, a); break;
-    default: launch_rollout_s<8>(h, a); break;
-  }
+  // the FAST variant needs: own noise, no taps, no obstacle term, a full last lane, TMA stores, and every half-step
+  // heading increment inside the Taylor range of mppi_sincos_small: |h w / 2| <= c_w (|uL| + |uR|) / 2 with
+  // |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
+  const double u_bound = 2.0 * h->plan_abs_max + 5.78 * (a.sigL + a.sigR);
+  const bool fast = !a.external_noise && !a.capture && !a.obs_on && a.tma_store && h->T == h->S * h->G &&
+                    0.5 * std::fabs(a.c_w) * u_bound <= 0.125 && !h->force_generic;
+  launch_rollout(h, a, fast);
   B2N_CUDA(cudaGetLastError());
   if (e1) B2N_CUDA(cudaEventRecord(e1, h->stream));
   h->launches++;
@@ -153,7 +197,7 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   if (h->nranks > 1) {
     // local merge -> one allgather of [T][6] doubles -> identical update on every rank
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 1;
-    mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+    mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
     B2N_CUDA(cudaGetLastError());
     h->launches++;
     ncclResult_t r = ncclAllGather(h->d_merged, h->d_gathered, (size_t)h->T * 6, ncclDouble, h->comm, h->stream);
@@ -162,7 +206,7 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   } else {
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
   }
-  mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+  mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
   B2N_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -190,8 +234,7 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_REQUIRE(p.ul_var >= 0.0 && p.ur_var >= 0.0, B2N_ERR_INVALID_ARGUMENT, "control variances must be non-negative");
   const int T = static_cast<int>(p.horizon / p.dt);   // mppi.cpp:47, truncation included
   B2N_REQUIRE(T >= 1, B2N_ERR_INVALID_ARGUMENT, "horizon/dt gives %d steps", T);
-  B2N_REQUIRE(T <= 32 * kMppiMaxS, B2N_ERR_UNSUPPORTED, "steps = %d exceeds the %d the rollout kernel is built for", T,
-              32 * kMppiMaxS);
+  B2N_REQUIRE(T <= kMppiMaxT, B2N_ERR_UNSUPPORTED, "steps = %d exceeds the %d the rollout kernel is built for", T, kMppiMaxT);
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -204,8 +247,9 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   h->p = p;
   h->T = T;
   h->K = p.rollouts;
-  int S = (T + 31) / 32;
-  h->S = S <= 1 ? 1 : S <= 2 ? 2 : S <= 4 ? 4 : 8;
+  pick_shape(T, h->S, h->G);
+  h->plan_abs_max = std::fabs(p.max_wheel_vel);   // the plan starts at 0 and every update is clamped to +-max_wheel_vel
+  if (const char *env = std::getenv("B2N_MPPI_GENERIC")) h->force_generic = env[0] == '1';
   if (p.device >= 0) h->device = p.device; else cudaGetDevice(&h->device);
 
 #define B2N_TRY(expr)                                                                          \
@@ -229,12 +273,7 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   h->n_sm = prop.multiProcessorCount;
   B2N_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
-  switch (h->S) {
-    case 1: B2N_TRY(configure_s<1>(h)); break;
-    case 2: B2N_TRY(configure_s<2>(h)); break;
-    case 4: B2N_TRY(configure_s<4>(h)); break;
-    default: B2N_TRY(configure_s<8>(h)); break;
-  }
+  B2N_TRY(configure(h));
   h->tma_store = ((size_t)T * 3 * sizeof(float)) % 16 == 0;   // cp.async.bulk moves 16-byte granules
 
   const size_t KT = (size_t)h->K * T;
@@ -277,6 +316,7 @@ int b2n_mppi_set_initial_controls(b2n_mppi *h, double ul, double ur)
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
   if (int rc = set_device(h)) return rc;
   h->uinit[0] = ul; h->uinit[1] = ur;
+  h->plan_abs_max = std::max(h->plan_abs_max, std::max(std::fabs(ul), std::fabs(ur)));
   std::vector<double> u(2 * h->T);
   for (int t = 0; t < h->T; t++) { u[t] = ul; u[h->T + t] = ur; }
   B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -410,6 +450,7 @@ int b2n_mppi_set_plan(b2n_mppi *h, const double *u, size_t count)
   B2N_REQUIRE(h && u, B2N_ERR_INVALID_ARGUMENT, "null argument");
   B2N_REQUIRE(count == (size_t)2 * h->T, B2N_ERR_INVALID_ARGUMENT, "plan count %zu, expected 2*T = %d", count, 2 * h->T);
   if (int rc = set_device(h)) return rc;
+  for (size_t i = 0; i < count; i++) h->plan_abs_max = std::max(h->plan_abs_max, std::fabs(u[i]));
   B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   return B2N_OK;
@@ -424,7 +465,7 @@ int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count)
   std::memset(&u, 0, sizeof(u));
   u.T = h->T; u.inv_lambda = 1.0 / h->p.lambda; u.partials = h->d_partials; u.n_partials = h->grid;
   u.merge_only = 1; u.merged = h->d_merged;
-  mppi_update_kernel<<<h->T, 32, 0, h->stream>>>(u);
+  mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
   return copy_out(h, out, h->d_merged, count * sizeof(double));

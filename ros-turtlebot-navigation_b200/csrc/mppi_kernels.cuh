@@ -6,20 +6,22 @@
 // (diff-drive cart model), :87-105 (running / terminal loss).
 //
 // Design (DESIGN.md "MPPI"):
-//   * ONE WARP PER ROLLOUT.  Lane l owns the S consecutive time steps [l*S, l*S+S).  The cart model's
-//     heading rate does not depend on the state, so theta_t is a prefix sum of per-step increments
-//     and (x_t, y_t) a prefix sum of increments that depend only on theta_{t-1} and the step's
-//     controls: three warp-shuffle scans replace the T-long serial recurrence, and a reverse scan
-//     gives the cost-to-go (cumSumCost).  All of it in fp64 registers - the shipped cost weights
-//     (Q = 1e4, lambda = 0.01) make the softmax ill-conditioned in anything narrower.
-//   * noise is counter-based (Philox4x32-10 keyed by seed, call, rollout, step), generated in
-//     registers; nothing is read from HBM except the 2*T plan.
-//   * the only mandatory HBM traffic is the fp32 [K][T][3] state tensor: each warp stages its row in
-//     shared memory and one lane hands it to the TMA unit (cp.async.bulk shared->global), double
-//     buffered so the next rollout's math overlaps the store.
+//   * WARP-COOPERATIVE ROLLOUTS.  A group of G lanes (8, 16 or the whole warp, chosen so that every lane
+//     owns S = 2, 4 or 8 consecutive time steps) carries one rollout; the cart model's heading rate does not
+//     depend on the state, so the T-long serial RK4 recurrence collapses into segmented warp scans: the
+//     heading is a prefix sum, its sine / cosine a prefix PRODUCT of per-step rotations (each from a short
+//     Taylor series of the half-step angle - no full-range sincos anywhere), the position a prefix sum of
+//     increments, the cost-to-go a suffix sum (cumSumCost).  All in fp64 registers - the shipped cost
+//     weights (Q = 1e4, lambda = 0.01) make the softmax ill-conditioned in anything narrower.
+//   * noise is counter-based (Philox4x32-10 keyed by seed, call, rollout, step pair) and generated in
+//     registers: one Philox call feeds four binary32 Box-Muller variates (two steps x two wheels) built
+//     from correctly-rounded operations only, so the CPU oracle reproduces them bit for bit.
+//   * the only mandatory HBM traffic is the fp32 [K][T][3] state tensor: each warp stages its rows in
+//     shared memory and one lane hands them to the TMA unit (cp.async.bulk shared->global), double
+//     buffered so the next rollouts' math overlaps the store.
 //   * the T softmaxes are carried ONLINE: every lane keeps (min J, sum e, sum e*duL, sum e*duR,
-//     sum duL, sum duR) for its S steps across all rollouts of its warp, warps merge through shared
-//     memory, each CTA writes one [T][6] partial.  J never makes a round trip through HBM.
+//     sum duL, sum duR) for its S steps across all rollouts it sees, lane groups and warps merge at the
+//     end, each CTA writes one [T][6] partial.  J never makes a round trip through HBM.
 //   * mppi_update_kernel merges the partials (from all CTAs, or from all ranks after the allgather),
 //     applies the weighted update, clamps, emits the first control and shifts the plan.
 #pragma once
@@ -29,16 +31,16 @@
 namespace b2n
 {
 
-constexpr int kMppiThreads = 256;            // 8 warps = 8 rollouts in flight per CTA
+constexpr int kMppiThreads = 256;            // 8 warps per CTA
 constexpr int kMppiWarps = kMppiThreads / 32;
-constexpr int kMppiMaxS = 8;                 // T <= 256
+constexpr int kMppiMaxT = 256;               // 32 lanes x 8 steps
 
 struct MppiArgs
 {
   // model, cost, sampling
-  double r_half, r_over_L;
+  double c_v, c_w;            // (r/2)(h/6) and (r/L) h: position and heading increment factors (mppi.hpp:45-47, rk4.cpp:114)
   double Q[3], R[2], P1[3];
-  double inv_lambda, h, h_sixth, sigL, sigR;
+  double inv_lambda, sigL, sigR;
   double x0[3], xd[3];
   int T, K, k_offset;
   uint32_t seed_lo, seed_hi, call;
@@ -81,248 +83,344 @@ __device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, double x
   return pen > 0.0 ? a.obs_weight * pen * pen : 0.0;
 }
 
-template <int S>
-__global__ void __launch_bounds__(kMppiThreads) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+// exp(x) for x <= 0.  Below -708 the result is subnormal or zero: added to a softmax sum that already holds the
+// minimum's 1.0 it cannot change a bit, so the evaluation is skipped (at the shipped lambda = 0.01 that is almost
+// every term).
+__device__ __forceinline__ double mppi_exp_neg(double x) { return x > -708.0 ? exp(x) : 0.0; }
+
+// sin and cos of a small angle by Taylor series (|d| <= 1/8: truncation < 3e-16 relative); full range falls back
+template <bool ALWAYS_SMALL>
+__device__ __forceinline__ void mppi_sincos_small(double d, double &sn, double &cs)
 {
-  constexpr int SLOTS = 32 * S;
+  if (!ALWAYS_SMALL && fabs(d) > 0.125) { sincos(d, &sn, &cs); return; }
+  const double z = d * d;
+  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
+  ps = fma(z, ps, 8.3333333333333332e-03);                                // 1/5!
+  ps = fma(z, ps, -1.6666666666666666e-01);                               // -1/3!
+  sn = fma(d * z, ps, d);
+  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);    // -1/10!, 1/8!
+  pc = fma(z, pc, -1.3888888888888889e-03);                               // -1/6!
+  pc = fma(z, pc, 4.1666666666666664e-02);                                // 1/4!
+  pc = fma(z, pc, -0.5);
+  cs = fma(z, pc, 1.0);
+}
+
+// dynamic shared memory: [warps][2][32*S*3] fp32 staging rows, then [S*6][threads] fp64 online-softmax accumulators
+// (kept out of the register file so that three CTAs fit an SM; reused as [warps][G*S][6] for the CTA merge)
+__host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G)
+{
+  return (size_t)kMppiWarps * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * kMppiThreads * sizeof(double);
+}
+
+// FAST = the production configuration, decided on the host: own noise, no capture taps, no obstacle term, T == G * S
+// (no partially filled lanes), TMA row stores, and half-step heading increments provably inside the Taylor range.
+template <int S, int G, bool FAST>
+__global__ void __launch_bounds__(kMppiThreads, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+{
+  static_assert(S % 2 == 0 && (G == 8 || G == 16 || G == 32), "a Philox call covers two steps; G lanes per rollout");
+  constexpr int R = 32 / G;        // rollouts a warp carries at a time
+  constexpr int TP = G * S;        // padded horizon
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *stage_base = reinterpret_cast<float *>(smem_raw);                                  // [warps][2][SLOTS*3]
-  double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * SLOTS * 3 * 4);  // [SLOTS][6]
+  float *stage_base = reinterpret_cast<float *>(smem_raw);                                       // [warps][2][R*TP*3]
+  double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
+  double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4);             // [warps][TP][6] (epilogue)
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int g = lane & (G - 1);    // position inside the rollout's lane group
+  const int r = lane / G;          // which of the warp's R rollouts
   const int gw = blockIdx.x * kMppiWarps + warp;
   const int nw = gridDim.x * kMppiWarps;
-  const int T = a.T;
-  float *stage = stage_base + warp * 2 * SLOTS * 3;
+  const int T = FAST ? TP : a.T;
+  const int t0 = g * S;            // first owned step
+  const bool ext_noise = !FAST && a.external_noise, capture = !FAST && a.capture, obs_on = !FAST && a.obs_on;
+  const bool tma_store = FAST || a.tma_store;
+  float *stage = stage_base + warp * 2 * (R * TP * 3);
 
-  // the lane's slice of the plan, resident for the whole kernel
-  double up0[S], up1[S];
-  bool act[S];
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    const int t = lane * S + s;
-    act[s] = t < T;
-    up0[s] = act[s] ? __ldg(&a.u_plan[t]) : 0.0;
-    up1[s] = act[s] ? __ldg(&a.u_plan[T + t]) : 0.0;
-  }
   double sin0, cos0;
   sincos(a.x0[2], &sin0, &cos0);
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
 
-  // online-softmax accumulators of this lane's steps
-  double am[S], aS[S], aA[S], aB[S], aDL[S], aDR[S];
+  // online-softmax accumulators of this lane's steps: (min J, sum e, sum e*duL, sum e*duR, sum duL, sum duR) x S
 #pragma unroll
   for (int s = 0; s < S; s++) {
-    am[s] = __longlong_as_double(0x7FF0000000000000LL);
-    aS[s] = aA[s] = aB[s] = aDL[s] = aDR[s] = 0.0;
+    acc[(s * 6 + 0) * kMppiThreads] = inf;
+#pragma unroll
+    for (int j = 1; j < 6; j++) acc[(s * 6 + j) * kMppiThreads] = 0.0;
   }
 
   int buf = 0;
-  for (int k = gw; k < a.K; k += nw, buf ^= 1) {
-    // ---- perturbed controls (mppi.cpp:84-93,173-184) and per-step kinematic terms ------------
-    double duL[S], duR[S], uL[S], uR[S], om[S], vv[S], dth[S];
+  for (int base = gw * R; base < a.K; base += nw * R, buf ^= 1) {
+    const int k = base + r;
+    const bool live = k < a.K;
+
+    // ---- perturbed controls (mppi.cpp:84-93,173-184), per-step increments, half-step rotations ----------
+    double duL[S], duR[S], cc[S], vh[S], dth[S], cd[S], sd[S];
+    double tc = 1.0, ts = 0.0, tth = 0.0;      // this lane's total rotation and heading change
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int t = lane * S + s;
-      double z0 = 0.0, z1 = 0.0;
-      if (a.external_noise) {
-        if (act[s]) {
-          const double2 e = __ldg(reinterpret_cast<const double2 *>(a.ext) + ((size_t)k * T + t));
-          z0 = e.x; z1 = e.y;
+    for (int s = 0; s < S; s += 2) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!ext_noise)
+        normal_quad_f32(a.seed_lo, a.seed_hi, kDomainMppi, a.call, (uint32_t)(a.k_offset + k), (uint32_t)((t0 + s) >> 1), z);
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int t = t0 + s + j;
+        const bool act = FAST || t < T;
+        double l = 0.0, rr = 0.0, p0 = 0.0, p1 = 0.0;
+        if (act) {
+          p0 = __ldg(&a.u_plan[t]);
+          p1 = __ldg(&a.u_plan[T + t]);
+          if (ext_noise) {
+            if (live) {
+              const double2 e = __ldg(reinterpret_cast<const double2 *>(a.ext) + ((size_t)k * T + t));
+              l = e.x; rr = e.y;
+            }
+          } else {
+            l = (double)z[2 * j] * a.sigL;
+            rr = (double)z[2 * j + 1] * a.sigR;
+          }
         }
-        duL[s] = z0; duR[s] = z1;
-      } else {
-        normal_pair(a.seed_lo, a.seed_hi, kDomainMppi, a.call, (uint32_t)(a.k_offset + k), (uint32_t)t, z0, z1);
-        duL[s] = act[s] ? z0 * a.sigL : 0.0;
-        duR[s] = act[s] ? z1 * a.sigR : 0.0;
+        duL[s + j] = l; duR[s + j] = rr;
+        const double uL = p0 + l, uR = p1 + rr;                 // NOT clamped (mppi.cpp:93)
+        cc[s + j] = (uL * a.R[0]) * uL + (uR * a.R[1]) * uR;    // u^T R u (mppi.hpp:92)
+        vh[s + j] = a.c_v * (uL + uR);                          // (h/6) v, v = (r/2)(uL + uR)   (mppi.hpp:45-46)
+        dth[s + j] = a.c_w * (uR - uL);                         // h w, w = (r/L)(uR - uL): rk4.cpp:114 with k1 = k2 = k3 = k4
+        mppi_sincos_small<FAST>(0.5 * dth[s + j], sd[s + j], cd[s + j]);
+        // full-step rotation, folded into the lane total
+        const double c2 = fma(cd[s + j], cd[s + j], -(sd[s + j] * sd[s + j])), s2 = 2.0 * (sd[s + j] * cd[s + j]);
+        const double nc = tc * c2 - ts * s2;
+        ts = fma(tc, s2, ts * c2);
+        tc = nc;
+        tth += dth[s + j];
       }
-      uL[s] = up0[s] + duL[s];            // NOT clamped (mppi.cpp:93)
-      uR[s] = up1[s] + duR[s];
-      vv[s] = a.r_half * (uL[s] + uR[s]); // mppi.hpp:45-46
-      om[s] = a.r_over_L * (uR[s] - uL[s]);   // mppi.hpp:47
-      // rk4.cpp:114 on the theta component: (h/6)(k1 + 2k2 + 2k3 + k4) with all four equal to om
-      dth[s] = act[s] ? a.h_sixth * (om[s] + 2.0 * om[s] + 2.0 * om[s] + om[s]) : 0.0;
     }
 
-    // ---- theta: prefix sum over the horizon ----------------------------------------------------
-    double th_off[S];
-    double run = 0.0;
+    // ---- segmented inclusive scans over the rollout's G lanes: rotation product and heading sum ----------
 #pragma unroll
-    for (int s = 0; s < S; s++) { th_off[s] = run; run += dth[s]; }
-    double incl = warp_inclusive_sum(run, lane);
-    double excl = __shfl_up_sync(kFullMask, incl, 1);
-    if (lane == 0) excl = 0.0;
-
-    // ---- RK4 stage angles: k1 at theta, k2 = k3 at theta + h/2*om, k4 at theta + h*om ----------
-    double cm[S], sm[S], ce[S], se[S], tha[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      tha[s] = a.x0[2] + (excl + th_off[s]);                 // heading at the start of step t
-      sincos(tha[s] + a.h * (0.5 * om[s]), &sm[s], &cm[s]);  // rk4.cpp:105-109
-      sincos(tha[s] + a.h * om[s], &se[s], &ce[s]);          // rk4.cpp:111-112
-    }
-    // the k4 angle of step t is the k1 angle of step t+1 to within an ulp: reuse its sin/cos
-    double ca_first = __shfl_up_sync(kFullMask, ce[S - 1], 1);
-    double sa_first = __shfl_up_sync(kFullMask, se[S - 1], 1);
-    if (lane == 0) { ca_first = cos0; sa_first = sin0; }
-
-    double dx[S], dy[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const double ca = (s == 0) ? ca_first : ce[s == 0 ? 0 : s - 1];
-      const double sa = (s == 0) ? sa_first : se[s == 0 ? 0 : s - 1];
-      const double k1x = vv[s] * ca, k23x = vv[s] * cm[s], k4x = vv[s] * ce[s];
-      const double k1y = vv[s] * sa, k23y = vv[s] * sm[s], k4y = vv[s] * se[s];
-      dx[s] = act[s] ? a.h_sixth * (k1x + 2.0 * k23x + 2.0 * k23x + k4x) : 0.0;   // rk4.cpp:114
-      dy[s] = act[s] ? a.h_sixth * (k1y + 2.0 * k23y + 2.0 * k23y + k4y) : 0.0;
-    }
-
-    // ---- position: prefix sums -------------------------------------------------------------------
-    double px[S], py[S];
-    double rx = 0.0, ry = 0.0;
-#pragma unroll
-    for (int s = 0; s < S; s++) { rx += dx[s]; ry += dy[s]; px[s] = rx; py[s] = ry; }
-    double ix = warp_inclusive_sum(rx, lane), iy = warp_inclusive_sum(ry, lane);
-    double ex = __shfl_up_sync(kFullMask, ix, 1), ey = __shfl_up_sync(kFullMask, iy, 1);
-    if (lane == 0) { ex = 0.0; ey = 0.0; }
-
-    // ---- states after each step, loss (mppi.cpp:99-105, mppi.hpp:87-105) ----------------------
-    double X[S], Y[S], TH[S], loss[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int t = lane * S + s;
-      X[s] = a.x0[0] + (ex + px[s]);
-      Y[s] = a.x0[1] + (ey + py[s]);
-      TH[s] = tha[s] + dth[s];
-      const double e0 = X[s] - a.xd[0], e1 = Y[s] - a.xd[1], e2 = TH[s] - a.xd[2];   // theta NOT wrapped
-      double l;
-      if (t < T - 1) {
-        l = ((e0 * a.Q[0]) * e0 + (e1 * a.Q[1]) * e1 + (e2 * a.Q[2]) * e2) +
-            ((uL[s] * a.R[0]) * uL[s] + (uR[s] * a.R[1]) * uR[s]);
-      } else {
-        l = (e0 * a.P1[0]) * e0 + (e1 * a.P1[1]) * e1 + (e2 * a.P1[2]) * e2;   // replaces the running loss
+    for (int d = 1; d < G; d <<= 1) {
+      const double oc = __shfl_up_sync(kFullMask, tc, d, G), os = __shfl_up_sync(kFullMask, ts, d, G);
+      const double ot = __shfl_up_sync(kFullMask, tth, d, G);
+      if (g >= d) {
+        const double nc = tc * oc - ts * os;
+        ts = fma(tc, os, ts * oc);
+        tc = nc;
+        tth += ot;
       }
-      if (a.obs_on) l += mppi_obstacle_cost(a, X[s], Y[s]);
-      loss[s] = act[s] ? l : 0.0;
+    }
+    // exclusive prefix, seeded with the start heading
+    double rc = __shfl_up_sync(kFullMask, tc, 1, G), rs = __shfl_up_sync(kFullMask, ts, 1, G);
+    double th = __shfl_up_sync(kFullMask, tth, 1, G);
+    if (g == 0) { rc = 1.0; rs = 0.0; th = 0.0; }
+    {
+      const double nc = rc * cos0 - rs * sin0;
+      rs = fma(rc, sin0, rs * cos0);
+      rc = nc;
     }
 
-    // ---- cost-to-go: suffix sums (cumSumCost, mppi.cpp:15-25) -----------------------------------
+    // ---- RK4 position increments: k1 at theta, k2 = k3 at theta + h w / 2, k4 at theta + h w (rk4.cpp:95-115) ----
+    double px[S], py[S], TH[S];
+    double ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const double mc = rc * cd[s] - rs * sd[s], ms = fma(rc, sd[s], rs * cd[s]);      // mid-step heading
+      const double ec = mc * cd[s] - ms * sd[s], es = fma(mc, sd[s], ms * cd[s]);      // end-of-step heading
+      ax = fma(vh[s], fma(4.0, mc, rc + ec), ax);      // (h/6) v (k1 + 2 k2 + 2 k3 + k4), running sum inside the lane
+      ay = fma(vh[s], fma(4.0, ms, rs + es), ay);
+      px[s] = ax; py[s] = ay;
+      th += dth[s];
+      TH[s] = a.x0[2] + th;
+      rc = ec; rs = es;
+    }
+
+    // ---- position: segmented prefix sums -------------------------------------------------------------------
+    double ix = ax, iy = ay;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const double ox = __shfl_up_sync(kFullMask, ix, d, G), oy = __shfl_up_sync(kFullMask, iy, d, G);
+      if (g >= d) { ix += ox; iy += oy; }
+    }
+    double ex = __shfl_up_sync(kFullMask, ix, 1, G), ey = __shfl_up_sync(kFullMask, iy, 1, G);
+    if (g == 0) { ex = 0.0; ey = 0.0; }
+    ex += a.x0[0]; ey += a.x0[1];
+
+    // ---- states after each step -> staging row; loss (mppi.cpp:99-105, mppi.hpp:87-105) -------------------
+    float *row = stage + buf * (R * TP * 3) + r * (T * 3);
+    if (tma_store) {
+      if (lane == 0) tma_store_wait_read<1>();   // the store issued two passes ago has drained this buffer
+      __syncwarp();
+    }
     double J[S];
     double rj = 0.0;
 #pragma unroll
-    for (int s = S - 1; s >= 0; s--) { rj += loss[s]; J[s] = rj; }
-    double ij = warp_inclusive_suffix_sum(rj, lane);
-    double ej = __shfl_down_sync(kFullMask, ij, 1);
-    if (lane == 31) ej = 0.0;
-#pragma unroll
-    for (int s = 0; s < S; s++) J[s] += ej;
-
-    // ---- online softmax over rollouts, one accumulator set per owned step ---------------------
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      if (act[s]) {
-        const double d = (am[s] - J[s]) * a.inv_lambda;     // > 0: J is the new minimum
-        const double e = exp(-fabs(d));
-        const bool newmin = d > 0.0;
-        aS[s] = newmin ? fma(aS[s], e, 1.0) : aS[s] + e;
-        aA[s] = newmin ? fma(aA[s], e, duL[s]) : fma(e, duL[s], aA[s]);
-        aB[s] = newmin ? fma(aB[s], e, duR[s]) : fma(e, duR[s], aB[s]);
-        am[s] = fmin(am[s], J[s]);
-        aDL[s] += duL[s];
-        aDR[s] += duR[s];
+    for (int s = S - 1; s >= 0; s--) {
+      const int t = t0 + s;
+      const double X = ex + px[s], Y = ey + py[s];
+      double l = 0.0;
+      if (FAST || t < T) {
+        row[t * 3 + 0] = (float)X;
+        row[t * 3 + 1] = (float)Y;
+        row[t * 3 + 2] = (float)TH[s];
+        const double e0 = X - a.xd[0], e1 = Y - a.xd[1], e2 = TH[s] - a.xd[2];   // theta NOT wrapped
+        if (t < T - 1) l = ((e0 * a.Q[0]) * e0 + (e1 * a.Q[1]) * e1 + (e2 * a.Q[2]) * e2) + cc[s];
+        else l = (e0 * a.P1[0]) * e0 + (e1 * a.P1[1]) * e1 + (e2 * a.P1[2]) * e2;   // replaces the running loss
+        if (obs_on) l += mppi_obstacle_cost(a, X, Y);
       }
+      rj += l;
+      J[s] = rj;                                  // suffix sum inside the lane (cumSumCost, mppi.cpp:15-25)
     }
 
-    // ---- optional capture for the parity taps ------------------------------------------------------
-    if (a.capture) {
+    // ---- cost-to-go: segmented suffix sum over the lanes ---------------------------------------------------
+    double ij = rj;
 #pragma unroll
-      for (int s = 0; s < S; s++) {
-        const int t = lane * S + s;
-        if (act[s]) {
-          a.J_out[(size_t)k * T + t] = J[s];
-          reinterpret_cast<double2 *>(a.du_out)[(size_t)k * T + t] = make_double2(duL[s], duR[s]);
+    for (int d = 1; d < G; d <<= 1) {
+      const double oj = __shfl_down_sync(kFullMask, ij, d, G);
+      if (g + d < G) ij += oj;
+    }
+    double ej = __shfl_down_sync(kFullMask, ij, 1, G);
+    if (g == G - 1) ej = 0.0;
+
+    // ---- online softmax over rollouts, one accumulator set per owned step ---------------------------------
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const double Js = J[s] + ej;
+      if (live && (FAST || t0 + s < T)) {
+        double *c = acc + s * 6 * kMppiThreads;
+        const double m0 = c[0];
+        const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
+        const double e = mppi_exp_neg(-fabs(d));
+        const bool newmin = d > 0.0;
+        const double S0 = c[kMppiThreads], A0 = c[2 * kMppiThreads], B0 = c[3 * kMppiThreads];
+        c[kMppiThreads] = newmin ? fma(S0, e, 1.0) : S0 + e;
+        c[2 * kMppiThreads] = newmin ? fma(A0, e, duL[s]) : fma(e, duL[s], A0);
+        c[3 * kMppiThreads] = newmin ? fma(B0, e, duR[s]) : fma(e, duR[s], B0);
+        if (newmin) c[0] = Js;
+        c[4 * kMppiThreads] += duL[s];
+        c[5 * kMppiThreads] += duR[s];
+        if (capture) {
+          a.J_out[(size_t)k * T + t0 + s] = Js;
+          reinterpret_cast<double2 *>(a.du_out)[(size_t)k * T + t0 + s] = make_double2(duL[s], duR[s]);
         }
       }
     }
 
-    // ---- the state tensor: stage the row, hand it to the TMA unit ----------------------------
-    float *row = stage + buf * SLOTS * 3;
-    if (a.tma_store) {
-      if (lane == 0) tma_store_wait_read<1>();   // the store issued two rollouts ago has drained this buffer
-      __syncwarp();
-    }
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int t = lane * S + s;
-      row[t * 3 + 0] = (float)X[s];
-      row[t * 3 + 1] = (float)Y[s];
-      row[t * 3 + 2] = (float)TH[s];
-    }
-    float *grow = a.states + (size_t)k * T * 3;
-    if (a.tma_store) {
+    // ---- the state tensor: the warp's rows are contiguous in [K][T][3]; one bulk store ---------------------
+    const int nlive = min(R, a.K - base);
+    float *gdst = a.states + (size_t)base * T * 3;
+    const float *ssrc = stage + buf * (R * TP * 3);
+    if (tma_store) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_1d(grow, row, (uint32_t)(T * 3 * sizeof(float)));
+        tma_store_1d(gdst, ssrc, (uint32_t)(nlive * T * 3 * sizeof(float)));
         tma_store_commit();
       }
     } else {
       __syncwarp();
-      for (int i = lane; i < T * 3; i += 32) grow[i] = row[i];
+      for (int i = lane; i < nlive * T * 3; i += 32) gdst[i] = ssrc[i];
       __syncwarp();
     }
   }
-  if (a.tma_store && lane == 0) tma_store_wait<0>();
+  if (tma_store && lane == 0) tma_store_wait<0>();
 
-  // ---- merge the warps' accumulators in shared memory, one warp at a time -------------------
-  for (int w = 0; w < kMppiWarps; w++) {
-    if (warp == w) {
+  // ---- merge the CTA's accumulator sets per time step: minimum first, then every set rescaled ONCE -----------------
+  // (two passes instead of pairwise softmax merges: one exponential per set, all of them independent).  Lane groups
+  // of a warp combine by xor-shuffles, warps through shared memory laid out [.][warp][g] so that lanes read
+  // consecutive words.
+  double am[S], aS[S], aA[S], aB[S], aDL[S], aDR[S];
 #pragma unroll
-      for (int s = 0; s < S; s++) {
-        double *c = cta_acc + (lane * S + s) * 6;
-        if (w == 0) {
-          c[0] = am[s]; c[1] = aS[s]; c[2] = aA[s]; c[3] = aB[s]; c[4] = aDL[s]; c[5] = aDR[s];
-        } else {
-          const double m0 = c[0], m1 = am[s];
-          const double m = fmin(m0, m1);
-          // an empty accumulator has min = +inf and zero sums; exp(-inf) = 0 keeps it out
-          const double f0 = (m0 == m) ? 1.0 : exp((m - m0) * a.inv_lambda);
-          const double f1 = (m1 == m) ? 1.0 : exp((m - m1) * a.inv_lambda);
-          c[0] = m;
-          c[1] = c[1] * f0 + aS[s] * f1;
-          c[2] = c[2] * f0 + aA[s] * f1;
-          c[3] = c[3] * f0 + aB[s] * f1;
-          c[4] += aDL[s];
-          c[5] += aDR[s];
-        }
-      }
-    }
-    __syncthreads();
+  for (int s = 0; s < S; s++) {
+    const double *c = acc + s * 6 * kMppiThreads;
+    am[s] = c[0]; aS[s] = c[kMppiThreads]; aA[s] = c[2 * kMppiThreads]; aB[s] = c[3 * kMppiThreads];
+    aDL[s] = c[4 * kMppiThreads]; aDR[s] = c[5 * kMppiThreads];
   }
-  double *out = a.partials + (size_t)blockIdx.x * T * 6;
-  for (int i = threadIdx.x; i < T * 6; i += kMppiThreads) out[i] = cta_acc[i];
+  double *smin = reinterpret_cast<double *>(smem_raw);     // [S][warps][G], over the staging rows
+  double *ssum = cta_acc;                                   // [S][warps][5][G], over the accumulator area
+  __syncthreads();      // every warp has left the loop and drained its bulk stores: the staging rows are free
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    double m = am[s];
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) m = fmin(m, __shfl_xor_sync(kFullMask, m, off));
+    if (r == 0) smin[(s * kMppiWarps + warp) * G + g] = m;
+  }
+  __syncthreads();      // every thread has read its accumulators: their area may be overwritten from here on
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    double m = smin[(s * kMppiWarps) * G + g];
+#pragma unroll
+    for (int w = 1; w < kMppiWarps; w++) m = fmin(m, smin[(s * kMppiWarps + w) * G + g]);
+    // an empty set has min = +inf and zero sums
+    const double f = (am[s] == inf) ? 0.0 : ((am[s] == m) ? 1.0 : mppi_exp_neg((m - am[s]) * a.inv_lambda));
+    double v[5] = {aS[s] * f, aA[s] * f, aB[s] * f, aDL[s], aDR[s]};
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+#pragma unroll
+      for (int off = G; off < 32; off <<= 1) v[j] += __shfl_xor_sync(kFullMask, v[j], off);
+      if (r == 0) ssum[((s * kMppiWarps + warp) * 5 + j) * G + g] = v[j];
+    }
+    am[s] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < TP) {
+    const int ss = threadIdx.x / G, gg = threadIdx.x % G;
+    const int t = gg * S + ss;
+    if (t < T) {
+      double m = smin[(ss * kMppiWarps) * G + gg];
+#pragma unroll
+      for (int w = 1; w < kMppiWarps; w++) m = fmin(m, smin[(ss * kMppiWarps + w) * G + gg]);
+      double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int w = 0; w < kMppiWarps; w++)
+#pragma unroll
+        for (int j = 0; j < 5; j++) v[j] += ssum[((ss * kMppiWarps + w) * 5 + j) * G + gg];
+      double *out = a.partials + ((size_t)blockIdx.x * T + t) * 6;
+      reinterpret_cast<double2 *>(out)[0] = make_double2(m, v[0]);
+      reinterpret_cast<double2 *>(out)[1] = make_double2(v[1], v[2]);
+      reinterpret_cast<double2 *>(out)[2] = make_double2(v[3], v[4]);
+    }
+  }
 }
 
-// One warp per time step: merge the partials, then (unless merge_only) the control update of
+// One CTA per time step: merge the partials, then (unless merge_only) the control update of
 // mppi.cpp:112-137 for that step, written one slot to the left (the receding-horizon shift).
-__global__ void __launch_bounds__(32) mppi_update_kernel(const MppiUpdateArgs a)
+constexpr int kMppiUpdateThreads = 128;
+
+__global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const MppiUpdateArgs a)
 {
+  __shared__ double red[kMppiUpdateThreads / 32][6];
   const int t = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = a.T;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
 
+  // phase 1: the step's minimum over all partials
   double m = inf;
-  for (int p = lane; p < a.n_partials; p += 32) m = fmin(m, a.partials[((size_t)p * T + t) * 6]);
+  for (int p = threadIdx.x; p < a.n_partials; p += kMppiUpdateThreads) m = fmin(m, a.partials[((size_t)p * T + t) * 6]);
   m = warp_min(m);
+  if (lane == 0) red[warp][0] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int w = 1; w < kMppiUpdateThreads / 32; w++) m = fmin(m, red[w][0]);
+  __syncthreads();
+  // phase 2: every partial rescaled once to that minimum (independent exponentials), plain sums
   double S = 0.0, A = 0.0, B = 0.0, DL = 0.0, DR = 0.0;
-  for (int p = lane; p < a.n_partials; p += 32) {
-    const double *c = a.partials + ((size_t)p * T + t) * 6;
-    const double f = (c[0] == m) ? 1.0 : exp((m - c[0]) * a.inv_lambda);
-    S += c[1] * f; A += c[2] * f; B += c[3] * f; DL += c[4]; DR += c[5];
+  for (int p = threadIdx.x; p < a.n_partials; p += kMppiUpdateThreads) {
+    const double2 *c = reinterpret_cast<const double2 *>(a.partials + ((size_t)p * T + t) * 6);
+    const double2 c0 = c[0], c1 = c[1], c2 = c[2];
+    if (c0.x != inf) {
+      const double f = (c0.x == m) ? 1.0 : mppi_exp_neg((m - c0.x) * a.inv_lambda);
+      S = fma(c0.y, f, S); A = fma(c1.x, f, A); B = fma(c1.y, f, B);
+    }
+    DL += c2.x; DR += c2.y;
   }
   S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
-  if (lane != 0) return;
+  if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < kMppiUpdateThreads / 32; w++) {
+    S += red[w][1]; A += red[w][2]; B += red[w][3]; DL += red[w][4]; DR += red[w][5];
+  }
 
   if (a.merge_only) {
     double *o = a.merged + (size_t)t * 6;
