@@ -6,6 +6,7 @@
 // Compiled with -fmad=false (see rbpf_kernels.cuh).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -39,7 +40,11 @@ struct b2n_pf
   bool ext_armed = false;
   double *d_samples = nullptr;        // [N][k][4]
   unsigned long long *d_spill = nullptr, *d_stats = nullptr;
-  int esdf_grid = 0, esdf_hcap = 2048;
+  // distance-field launch shape (configure_df): one CTA per SM, df_warps particles in flight per CTA
+  int df_grid = 0, df_warps = 1, df_hcap = 0, df_hcap_request = 0, df_gcap = 0, df_cols = 0;
+  bool df_tmem = true, df_tmem_active = true;
+  size_t df_smem = 0, spill_entries = 0;
+  size_t smem_optin = 0;
   double *d_best = nullptr, *h_best = nullptr;   // pose[3], weight
   int8_t *d_map = nullptr;
   double *d_lik = nullptr;
@@ -135,6 +140,45 @@ int upload_scan(b2n_pf *h, const float *scan, int n_beams)
   B2N_REQUIRE(n_beams <= h->max_beams, B2N_ERR_INVALID_ARGUMENT, "scan has %d beams, handle was created for %d", n_beams, h->max_beams);
   std::memcpy(h->h_scan, scan, sizeof(float) * n_beams);
   B2N_CUDA(cudaMemcpyAsync(h->d_scan, h->h_scan, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
+  return B2N_OK;
+}
+
+// Launch shape of the distance-field kernel (rbpf_kernels.cuh): one CTA per SM, one particle per warp, as many warps
+// as it takes to hold every particle of this handle in flight at once (at most 28 = 4144 chains on 148 SMs); the heap
+// of each warp gets an equal share of the SM's shared memory, the visited bitmap goes to tensor memory when each
+// warp's 32-lane slice of the 512 columns can hold it.
+int configure_df(b2n_pf *h)
+{
+  const PfConst &c = h->c;
+  int W = std::max(1, std::min(kDfMaxWarps, (h->N + h->n_sm - 1) / h->n_sm));
+  const int words = (c.G + 31) / 32;
+  const int cols_needed = (words + 31) / 32 + 1;
+  const size_t budget = h->smem_optin - 2048;     // static shared memory and alignment slack
+  bool tmem = h->df_tmem;
+  int hcap = 0, cols = 0;
+  for (;; W--) {
+    cols = 512 / ((W + 3) / 4);
+    const bool t = tmem && cols_needed <= cols;
+    const size_t per_warp = budget / W;
+    const size_t marks = t ? 0 : (size_t)words * 4;
+    hcap = per_warp > marks + 16 ? (int)((per_warp - marks) / 8) - 2 : 0;
+    hcap = std::min(hcap & ~1, 16384);
+    if (hcap >= 64 || W == 1) { tmem = t; break; }
+  }
+  B2N_REQUIRE(hcap >= 2, B2N_ERR_UNSUPPORTED, "the distance-field kernel does not fit this map in shared memory");
+  if (h->df_hcap_request > 0) hcap = std::min(hcap, h->df_hcap_request);
+  h->df_warps = W; h->df_hcap = hcap; h->df_cols = cols;
+  h->df_grid = std::max(1, std::min(h->n_sm, (h->N + W - 1) / W));
+  h->df_gcap = std::min(c.G, 16384);
+  h->df_smem = pf_df_smem_bytes(c.G, hcap, W, tmem);
+  const bool tmem_used = tmem;
+  const size_t need = (size_t)h->df_grid * W * h->df_gcap;
+  if (need > h->spill_entries) {
+    cudaFree(h->d_spill); h->d_spill = nullptr; h->spill_entries = 0;
+    B2N_CUDA(cudaMalloc(&h->d_spill, need * sizeof(unsigned long long)));
+    h->spill_entries = need;
+  }
+  h->df_tmem_active = tmem_used;
   return B2N_OK;
 }
 
@@ -321,17 +365,13 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
   B2N_TRY(cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)));
   B2N_TRY(cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(unsigned long long), h->stream));
 
-  // distance-field launch shape: one warp-CTA per particle in flight, as many as shared memory allows
-  {
-    // the limit is per function and process-wide: always the device maximum, never lowered by another handle
-    const size_t smem = pf_esdf_smem_bytes(c.G, h->esdf_hcap);
-    B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    int per_sm = 0;
-    B2N_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rbpf_distance_field_kernel, 32, smem));
-    per_sm = std::max(1, per_sm);
-    h->esdf_grid = std::max(1, std::min(h->N, per_sm * h->n_sm));
-    B2N_TRY(cudaMalloc(&h->d_spill, (size_t)h->esdf_grid * c.G * sizeof(unsigned long long)));
-  }
+  // distance-field launch shape
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  // the limit is per function and process-wide: always the device maximum, never lowered by another handle
+  B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
+  B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
+  if (const char *env = std::getenv("B2N_PF_DF_SMEM_MARKS")) h->df_tmem = env[0] != '1';
+  if (configure_df(h) != B2N_OK) { b2n_pf_destroy(h); return B2N_ERR_CUDA; }
   if (pf_smem_bytes(h->max_beams, c.pz_stage, kPfWarpsPerCta) > prop.sharedMemPerBlockOptin) {
     set_error("max_beams = %d needs more shared memory than the device has", h->max_beams);
     b2n_pf_destroy(h);
@@ -423,7 +463,13 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   if (h->timing) { B2N_CUDA(cudaEventRecord(h->ev[1], h->stream)); B2N_CUDA(cudaEventRecord(h->ev[2], h->stream)); }
 
   // euclideanSignedDistanceField at the end of every integrateScan (grid_mapper.cpp:181)
-  rbpf_distance_field_kernel<<<h->esdf_grid, 32, pf_esdf_smem_bytes(c.G, h->esdf_hcap), h->stream>>>(c, pl, h->esdf_hcap, h->d_spill, h->d_stats);
+  {
+    PfDfArgs d;
+    d.hcap = h->df_hcap; d.gcap = h->df_gcap; d.warps = h->df_warps; d.cols_per_warp = h->df_cols;
+    d.spill = h->d_spill; d.stats = h->d_stats; d.status = h->d_status;
+    if (h->df_tmem_active) rbpf_distance_field_kernel<true><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
+    else rbpf_distance_field_kernel<false><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
+  }
   B2N_CUDA(cudaGetLastError());
   h->launches++;
   if (h->timing) { B2N_CUDA(cudaEventRecord(h->ev[3], h->stream)); B2N_CUDA(cudaEventRecord(h->ev[4], h->stream)); }
@@ -456,6 +502,10 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   if (status & kPfStatusOffMap) {
     set_error("a beam end point or a particle pose left the map (reference: world2Grid / world2RowMajor throw, grid_mapper.cpp:817-825,854-862)");
     return B2N_ERR_OFF_MAP;
+  }
+  if (status & kDfStatusHeapOverflow) {
+    set_error("distance field: the brushfire heap outgrew its %d + %d entries", h->df_hcap, h->df_gcap);
+    return B2N_ERR_UNSUPPORTED;
   }
   if (status & kPfStatusNumeric) {
     set_error("eta is 0 or a zero variance reached pdfNormal (reference: particle_filter.cpp:577-580, grid_mapper.cpp:20-23)");
@@ -742,18 +792,8 @@ int b2n_pf_set_heap_capacity(b2n_pf *h, int entries)
   B2N_REQUIRE(h && entries >= 2 && entries <= 24576, B2N_ERR_INVALID_ARGUMENT, "heap capacity must be in [2, 24576]");
   if (int rc = set_device(h)) return rc;
   B2N_CUDA(cudaStreamSynchronize(h->stream));
-  h->esdf_hcap = entries & ~1;
-  const size_t smem = pf_esdf_smem_bytes(h->c.G, h->esdf_hcap);
-  int per_sm = 0;
-  B2N_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rbpf_distance_field_kernel, 32, smem));
-  per_sm = std::max(1, per_sm);
-  const int grid = std::max(1, std::min(h->N, per_sm * h->n_sm));
-  if (grid > h->esdf_grid) {
-    cudaFree(h->d_spill); h->d_spill = nullptr;
-    B2N_CUDA(cudaMalloc(&h->d_spill, (size_t)grid * h->c.G * sizeof(unsigned long long)));
-  }
-  h->esdf_grid = grid;
-  return B2N_OK;
+  h->df_hcap_request = entries & ~1;
+  return configure_df(h);
 }
 
 int b2n_pf_host_tables(const b2n_pf_params *params, double constants[4], double *beam_cs, size_t beam_count, double *pz, size_t pz_cap,

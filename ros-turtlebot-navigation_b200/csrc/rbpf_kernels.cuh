@@ -581,46 +581,136 @@ __global__ void __launch_bounds__(kPfWarpsPerCta * 32) rbpf_proposal_kernel(cons
 }
 
 // ---- distance field: the reference's brushfire (grid_mapper.cpp:272-435) ---------------------------------------------
-// One warp (= one CTA) per particle in flight.  Heap entry = d2 << 32 | source cell << 16 | cell; the comparator of
-// grid_mapper.hpp:104-111 (a.occ_dist > b.occ_dist) is the comparison of d2.  Entry i lives in slot i + 1 so
-// that the two children of a node share one 16-byte shared-memory word pair; entries beyond `hcap` spill to a
-// per-CTA global scratch.
+// The result depends on the ORDER in which a libstdc++ binary heap releases equal keys and on the pop-after-push quirk
+// of grid_mapper.cpp:399-431, so each particle's field is one serial chain of about G heap operations: the kernel is
+// bound by the latency of one chain step, not by bandwidth, and all that can be done is (a) run every particle's chain
+// at the same time and (b) make a step short.
+//   (a) ONE CTA PER SM with up to 28 warps, one particle per warp: 148 x 28 = 4144 chains in flight, a single wave for
+//       the 4096 particles of BASELINE configs[2].  That leaves 8 KB of shared memory per warp, which is spent on the
+//       heap alone; the visited bitmap (G bits = 5 KB at 200 x 200) lives in TENSOR MEMORY: each warp owns a
+//       32-lane x 73-column slice of the SM's 256 KB of TMEM (word w of the bitmap = lane w % 32 of column w / 32),
+//       read with tcgen05.ld (two adjacent columns cover the four neighbours of a cell), updated in registers and
+//       written back with tcgen05.st.  No tensor-core instruction is involved; TMEM is used as a scratchpad.
+//   (b) heap entry = d2 << 32 | ci << 24 | cj << 16 | si << 8 | sj (cell and claiming obstacle as byte coordinates: no
+//       division to decode); entry i lives in slot i + 1 so that both children of a node come in one 16-byte load;
+//       the comparator of grid_mapper.hpp:104-111 (a.occ_dist > b.occ_dist) is the comparison of the d2 words;
+//       every lane runs the heap code redundantly (broadcast loads, same-value stores), lanes 0-3 test the four
+//       neighbours; entries beyond the shared-memory capacity spill to a per-warp global area.
+constexpr int kDfMaxWarps = 28;
+constexpr int kDfStatusHeapOverflow = 4;
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t &r0, uint32_t &r1)
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r0)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(r0) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// shared-memory accessors on 32-bit shared addresses (one instruction each, no generic-pointer arithmetic)
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v)
+{
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Heap entry as two words: .y = key (squared cell distance), .x = ci << 24 | cj << 16 | si << 8 | sj.
+// Entry i lives in shared slot i + 1 (byte address sb + 8 (i + 1)) while i < hcap, else in the global spill area.
 struct HeapDev
 {
-  unsigned long long *s;   // shared, hcap + 2 slots
-  unsigned long long *g;   // global spill
-  int hcap, len;
-  __device__ __forceinline__ unsigned long long get(int i) const { return i < hcap ? s[i + 1] : g[i - hcap]; }
-  __device__ __forceinline__ void set(int i, unsigned long long v) { if (i < hcap) s[i + 1] = v; else g[i - hcap] = v; }
-  // std::__push_heap(first, hole, top = 0, value)
-  __device__ __forceinline__ void sift_up(int hole, unsigned long long value)
+  uint32_t sb;             // shared byte address of slot 0
+  uint2 *g;                // global spill
+  int hcap, gcap, len;
+  bool overflow;
+  __device__ __forceinline__ uint2 get(int i) const { return i < hcap ? lds64(sb + 8u * (uint32_t)(i + 1)) : g[min(i - hcap, gcap - 1)]; }
+  __device__ __forceinline__ void set(int i, uint2 v)
   {
-    const uint32_t vk = (uint32_t)(value >> 32);
+    if (i < hcap) sts64(sb + 8u * (uint32_t)(i + 1), v);
+    else if (i - hcap < gcap) g[i - hcap] = v;
+    else overflow = true;
+  }
+  // std::__push_heap(first, hole, top = 0, value), any storage
+  __device__ __forceinline__ void sift_up(int hole, uint2 value)
+  {
     while (hole > 0) {
       const int parent = (hole - 1) >> 1;
-      const unsigned long long pe = get(parent);
-      if ((uint32_t)(pe >> 32) > vk) { set(hole, pe); hole = parent; }
+      const uint2 pe = get(parent);
+      if (pe.y > value.y) { set(hole, pe); hole = parent; }
       else break;
     }
     set(hole, value);
   }
-  __device__ __forceinline__ void push(unsigned long long e) { sift_up(len, e); len++; }
-  // std::pop_heap + pop_back: __adjust_heap(first, 0, len - 1, last value)
-  __device__ __forceinline__ void pop()
+  // push while the whole heap (including the new entry) is in shared memory; returns true if the entry reached the root
+  __device__ __forceinline__ bool push_shared(uint2 e)
+  {
+    int hole = len++;
+    while (hole > 0) {
+      const int parent = (hole - 1) >> 1;
+      const uint2 pe = lds64(sb + 8u * (uint32_t)(parent + 1));
+      if (pe.y > e.y) { sts64(sb + 8u * (uint32_t)(hole + 1), pe); hole = parent; }
+      else break;
+    }
+    sts64(sb + 8u * (uint32_t)(hole + 1), e);
+    return hole == 0;
+  }
+  __device__ __forceinline__ void push_any(uint2 e) { sift_up(len, e); len++; }
+  // std::pop_heap + pop_back = __adjust_heap(first, 0, len - 1, last value), len >= 2, whole heap in shared memory
+  __device__ __forceinline__ void pop_shared()
+  {
+    const int L = --len;                                   // index of the last entry, >= 1
+    const uint2 value = lds64(sb + 8u * (uint32_t)(L + 1));
+    const int limit = (L - 1) >> 1;
+    int second = 0;
+    uint32_t hole_addr = sb + 8u;
+    uint2 above = make_uint2(0u, 0u);                      // the entry now sitting in the hole's parent
+    while (second < limit) {
+      second = 2 * second + 2;
+      const uint4 pr = lds128(sb + 8u * (uint32_t)second);            // entries second - 1 (x, y) and second (z, w)
+      const bool left = pr.w > pr.y;                                  // comp(right, left): take the left child
+      above = left ? make_uint2(pr.x, pr.y) : make_uint2(pr.z, pr.w);
+      second -= left ? 1 : 0;
+      sts64(hole_addr, above);
+      hole_addr = sb + 8u * (uint32_t)(second + 1);
+    }
+    if ((L & 1) == 0 && second == ((L - 2) >> 1)) {
+      second = 2 * second + 1;                                        // the only child, entry 2 (second + 1) - 1
+      above = lds64(sb + 8u * (uint32_t)(second + 1));
+      sts64(hole_addr, above);
+      hole_addr = sb + 8u * (uint32_t)(second + 1);
+    }
+    // __push_heap from the leaf: the parent of the hole is the entry just moved there
+    if (second > 0 && above.y > value.y) sift_up(second, value);
+    else sts64(hole_addr, value);
+  }
+  __device__ __forceinline__ void pop_any()
   {
     if (len > 1) {
       const int L = len - 1;
-      const unsigned long long value = get(L);
+      const uint2 value = get(L);
       int hole = 0, second = 0;
       while (second < (L - 1) / 2) {
         second = 2 * (second + 1);
-        unsigned long long r, l;
-        if (second < hcap) {
-          const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(&s[second]);   // slots second, second + 1 = entries second - 1, second
-          l = pr.x; r = pr.y;
-        } else { r = get(second); l = get(second - 1); }
-        unsigned long long mv = r;
-        if ((uint32_t)(r >> 32) > (uint32_t)(l >> 32)) { second--; mv = l; }
+        const uint2 r = get(second), l = get(second - 1);
+        uint2 mv = r;
+        if (r.y > l.y) { second--; mv = l; }
         set(hole, mv);
         hole = second;
       }
@@ -635,73 +725,152 @@ struct HeapDev
   }
 };
 
-__host__ __device__ inline size_t pf_esdf_smem_bytes(int G, int hcap) { return (size_t)(hcap + 2) * 8 + (size_t)((G + 31) / 32) * 4; }
+// dynamic shared memory of the distance-field kernel: [warps][hcap + 2] heap slots (+ [warps][words] visited bitmap
+// when it is not kept in tensor memory)
+__host__ __device__ inline size_t pf_df_smem_bytes(int G, int hcap, int warps, bool tmem_marks)
+{
+  return (size_t)warps * ((size_t)(hcap + 2) * 8 + (tmem_marks ? 0 : (size_t)((G + 31) / 32) * 4));
+}
 
-__global__ void __launch_bounds__(32) rbpf_distance_field_kernel(const __grid_constant__ PfConst c, const PfPlanes pl, int hcap,
-                                                                  unsigned long long *spill, unsigned long long *stats)
+struct PfDfArgs
+{
+  int hcap, gcap, warps, cols_per_warp;
+  unsigned long long *spill;   // [gridDim.x * warps][gcap]
+  unsigned long long *stats;
+  int *status;
+};
+
+template <bool TMEM_MARKS>
+__global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_kernel(const __grid_constant__ PfConst c, const PfPlanes pl,
+                                                                                   const PfDfArgs d)
 {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x;
-  HeapDev H;
-  H.s = reinterpret_cast<unsigned long long *>(smem);
-  H.g = spill + (size_t)blockIdx.x * c.G;
-  H.hcap = hcap;
-  uint32_t *marked = reinterpret_cast<uint32_t *>(smem + (size_t)(hcap + 2) * 8);
+  __shared__ uint32_t tmem_base_slot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int words = (c.G + 31) / 32;
   const int xs = c.xsize, ys = c.ysize, R = c.cell_radius;
-  unsigned long long iters = 0, heap_max = 0;
 
-  for (int p = blockIdx.x; p < c.N; p += gridDim.x) {
+  uint32_t tbase = 0;
+  if (TMEM_MARKS) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // this warp's slice: its lane quadrant (the hardware lets warp w touch lanes 32 (w % 4) .. + 31 only), its columns
+    tbase = tmem_base_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * d.cols_per_warp);
+  }
+
+  HeapDev H;
+  H.sb = smem_u32(smem) + (uint32_t)warp * (uint32_t)(d.hcap + 2) * 8u;
+  H.g = reinterpret_cast<uint2 *>(d.spill) + ((size_t)blockIdx.x * d.warps + warp) * d.gcap;
+  H.hcap = d.hcap; H.gcap = d.gcap; H.overflow = false;
+  uint32_t *marked = TMEM_MARKS ? nullptr : reinterpret_cast<uint32_t *>(smem + (size_t)d.warps * (d.hcap + 2) * 8) + (size_t)warp * words;
+  unsigned long long iters = 0;
+  int heap_max = 0;
+  // lanes 0..3 test (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
+  const int dI = lane == 0 ? -1 : lane == 2 ? 1 : 0, dJ = lane == 1 ? -1 : lane == 3 ? 1 : 0;
+  const int dIdx = dI * xs + dJ;
+  const uint32_t dEntry = ((uint32_t)dI << 24) + ((uint32_t)dJ << 16);   // added to ci << 24 | cj << 16 (no carry crosses: in bounds)
+  const bool tester = lane < 4;
+  const int R2 = R * R;
+
+  for (int p = blockIdx.x * d.warps + warp; p < c.N; p += gridDim.x * d.warps) {
     const PfParticle *me = pl.meta + p;
     if (me->n_occ == 0) continue;                                        // grid_mapper.cpp:335-338
     const uint16_t *nxt = pl.nxt + (size_t)p * c.nxt_stride;
     uint32_t *d2p = pl.d2 + (size_t)p * c.gstride;
-    for (int w = lane; w < words; w += 32) marked[w] = 0;
-    __syncwarp();
-    H.len = 0;
-    // seeds in the iteration order of occ_cells_ (:348-361); all of distance 0, so push_heap leaves them in place
-    for (uint32_t key = nxt[c.G]; key != kNil16; key = nxt[key]) {
-      if (lane == 0) { d2p[key] = 0; marked[key >> 5] |= 1u << (key & 31); }
-      H.push(((unsigned long long)key << 16) | key);
-    }
-    __syncwarp();
-    while (H.len > 0) {
-      const unsigned long long top = H.get(0);                          // Q.top(), :399
-      const int cell = (int)(top & 0xFFFFu), src = (int)((top >> 16) & 0xFFFFu);
-      const int ci = cell / xs, cj = cell - ci * xs, si = src / xs, sj = src - si * xs;
-      // lanes 0..3: (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
-      bool valid = false;
-      unsigned long long entry = 0;
-      if (lane < 4) {
-        const int ni = ci + (lane == 0 ? -1 : lane == 2 ? 1 : 0), nj = cj + (lane == 1 ? -1 : lane == 3 ? 1 : 0);
-        const bool inb = lane == 0 ? ci > 0 : lane == 1 ? cj > 0 : lane == 2 ? ci < xs - 1 : cj < ys - 1;
-        if (inb) {
-          const int idx = ni * xs + nj;                                  // grid2RowMajor
-          if (!((marked[idx >> 5] >> (idx & 31)) & 1u)) {
-            const int di = abs(ni - si), dj = abs(nj - sj);
-            const int d2 = di * di + dj * dj;
-            if (di < R && dj < R && d2 <= R * R) {                       // distances_.at() range, dist > cell_radius_
-              valid = true;
-              d2p[idx] = (uint32_t)d2;
-              atomicOr(&marked[idx >> 5], 1u << (idx & 31));
-              entry = ((unsigned long long)(uint32_t)d2 << 32) | ((unsigned long long)src << 16) | (unsigned long long)idx;
-            }
-          }
-        }
-      }
-      unsigned m = __ballot_sync(kFullMask, valid);
-      while (m) {
-        const int from = __ffs(m) - 1;
-        H.push(__shfl_sync(kFullMask, entry, from));
-        m &= m - 1;
-      }
-      if ((unsigned long long)H.len > heap_max) heap_max = H.len;
-      H.pop();                                                           // pops whatever is on top NOW, :431
-      iters++;
+    const int cols = (words + 31) / 32;
+    if (TMEM_MARKS) {
+      for (int col = 0; col <= cols; col++) tmem_st1(tbase + col, 0u);
+      tmem_wait_st();
+    } else {
+      for (int w = lane; w < words; w += 32) marked[w] = 0;
       __syncwarp();
     }
+    H.len = 0;
+    // seeds in the iteration order of occ_cells_ (:348-361); all of distance 0, so push_heap leaves them where they land
+    {
+      uint32_t col_cur = 0xFFFFFFFFu, wv = 0;     // TMEM: the bitmap column being filled (this lane's word of it)
+      for (uint32_t key = nxt[c.G]; key != kNil16; key = nxt[key]) {
+        const uint32_t ki = key / (uint32_t)xs, kj = key - ki * (uint32_t)xs;
+        if (TMEM_MARKS) {
+          const uint32_t w = key >> 5, col = w >> 5;
+          if (col != col_cur) {
+            if (col_cur != 0xFFFFFFFFu) { tmem_st1(tbase + col_cur, wv); tmem_wait_st(); }
+            uint32_t dummy;
+            tmem_ld2(tbase + col, wv, dummy);
+            col_cur = col;
+          }
+          if ((uint32_t)lane == (w & 31u)) wv |= 1u << (key & 31);
+        } else if (lane == 0) marked[key >> 5] |= 1u << (key & 31);
+        if (lane == 0) d2p[key] = 0;
+        H.set(H.len, make_uint2((ki << 24) | (kj << 16) | (ki << 8) | kj, 0u));
+        H.len++;
+      }
+      if (TMEM_MARKS && col_cur != 0xFFFFFFFFu) { tmem_st1(tbase + col_cur, wv); tmem_wait_st(); }
+    }
+    __syncwarp();
+    heap_max = max(heap_max, H.len);
+    uint32_t it = 0;
+    while (H.len > 0) {
+      const uint2 top = lds64(H.sb + 8u);                                 // Q.top(), :399 (entry 0 is always in shared memory)
+      const int ci = (int)(top.x >> 24), cj = (int)((top.x >> 16) & 0xFFu), si = (int)((top.x >> 8) & 0xFFu), sj = (int)(top.x & 0xFFu);
+      const int ni = ci + dI, nj = cj + dJ;
+      const bool inb = tester && (unsigned)ni < (unsigned)xs && (unsigned)nj < (unsigned)ys;
+      const int idx0 = ci * xs + cj;                                      // grid2RowMajor
+      const int idx = inb ? idx0 + dIdx : idx0;
+      uint32_t r0 = 0, r1 = 0, colA = 0, word;
+      if (TMEM_MARKS) {
+        colA = (uint32_t)max(idx0 - xs, 0) >> 10;                        // columns colA, colA + 1 hold all four neighbours
+        tmem_ld2(tbase + colA, r0, r1);
+        const uint32_t w = (uint32_t)idx >> 5;
+        const uint32_t v0 = __shfl_sync(kFullMask, r0, w & 31u), v1 = __shfl_sync(kFullMask, r1, w & 31u);
+        word = ((w >> 5) != colA) ? v1 : v0;
+      } else word = marked[idx >> 5];
+      const int di = ni - si, dj = nj - sj;
+      const int d2 = di * di + dj * dj;
+      // unmarked, inside distances_.at()'s range, not farther than cell_radius_
+      const bool valid = inb && !((word >> (idx & 31)) & 1u) && d2 <= R2 && max(abs(di), abs(dj)) < R;
+      if (valid) d2p[idx] = (uint32_t)d2;
+      const uint2 entry = make_uint2((top.x & 0xFFFFu) + (top.x & 0xFFFF0000u) + dEntry, (uint32_t)d2);
+      unsigned m = __ballot_sync(kFullMask, valid);
+      if (m) {
+        const bool shared_ok = H.len + 4 <= H.hcap;
+        do {
+          const int from = __ffs(m) - 1;
+          m &= m - 1;
+          const uint2 e = make_uint2(__shfl_sync(kFullMask, entry.x, from), __shfl_sync(kFullMask, entry.y, from));
+          const int eidx = __shfl_sync(kFullMask, idx, from);
+          if (TMEM_MARKS) {
+            const uint32_t w = (uint32_t)eidx >> 5;
+            if ((uint32_t)lane == (w & 31u)) {
+              if ((w >> 5) != colA) r1 |= 1u << (eidx & 31); else r0 |= 1u << (eidx & 31);
+            }
+          } else if (lane == 0) marked[eidx >> 5] |= 1u << (eidx & 31);
+          if (shared_ok) H.push_shared(e);
+          else H.push_any(e);
+        } while (m);
+        if (TMEM_MARKS) { tmem_st2(tbase + colA, r0, r1); tmem_wait_st(); }
+        else __syncwarp();
+        heap_max = max(heap_max, H.len);
+      }
+      // Q.pop() pops whatever is on top NOW (a pushed cell may be nearer than the current top), :431
+      if (H.len >= 2 && H.len <= H.hcap) H.pop_shared();
+      else H.pop_any();
+      it++;
+    }
+    iters += it;
   }
-  if (stats && lane == 0) { atomicAdd(&stats[0], iters); atomicMax(&stats[1], heap_max); }
+  if (d.stats && lane == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); }
+  if (H.overflow && lane == 0) atomicOr(d.status, kDfStatusHeapOverflow);
+  if (TMEM_MARKS) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_slot), "n"(512));
+  }
 }
 
 // ---- normalise, N_eff, low-variance walk (particle_filter.cpp:442-500) -----------------------------------------------

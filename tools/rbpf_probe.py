@@ -13,12 +13,13 @@ import _oracle as orc  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 scans = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-hcap = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
+hcap = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 pkg = _pkg.load()
 poses, twists = orc.circle_path(scans)
 rng = np.random.default_rng(4)
 f = pkg.bmapping.make_filter(orc.pf_params(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3)))
-f.setHeapCapacity(hcap)
+if hcap:
+    f.setHeapCapacity(hcap)
 f.seed(1)
 f.setKernelTiming(True)
 for i in range(scans):
