@@ -13,8 +13,8 @@ with one ncclAllGather.  Rank 0 prints ONE JSON line.
   e2e       the same metric through the public synchronous call (host pose in, host controls out,
             one stream synchronisation per step).
   roofline  the rollout kernel alone: algorithmic bytes (12 B per trajectory-step, the fp32 state
-            tensor) over its mean duration from CUDA events recorded around every launch in a
-            second pass over the same steps; peak from MEASURED_PEAKS.json.
+            tensor) over its mean duration, `steps` launches back to back between two CUDA events
+            on the launching stream in a second pass; peak from MEASURED_PEAKS.json.
   cpu_baseline  the CPU oracle port (oracle/liboracle_nav.so), one thread, on a bounded sample.
   --impl reference  times the UNMODIFIED reference controller::MPPI compiled at oracle/_ref
             (single thread: its RNG is one process-global engine) on bounded samples of the same
@@ -45,7 +45,7 @@ def workload_config(n_gpus):
     return {
         "workload": "MPPI K=16384 T=64 diff-drive, quadratic waypoint cost (BASELINE configs[1]), shipped cost params",
         "rollouts_per_gpu": K_ROLLOUTS, "rollouts_total": K_ROLLOUTS * n_gpus, "horizon_steps": 64,
-        "noise": "Philox4x32-10 counter-based, seed 42",
+        "noise": "Philox4x32-10 counter-based + binary32 Box-Muller, seed 42",
         "l2": "state tensor written round-robin into %d buffers (%.0f MB) > 126 MB L2" % (STATE_RING, STATE_RING * K_ROLLOUTS * 64 * 12 / 1e6),
         "sharding": "rollouts" if n_gpus > 1 else "none",
     }
@@ -355,14 +355,12 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
 
-    # ---- roofline pass: same steps, CUDA events around every rollout-kernel launch -----------------
-    mppi.setKernelTiming(True)
+    # ---- roofline pass: the rollout kernel alone, launched back to back between two CUDA events on the ------
+    # handle's stream (event pairs around single launches add ~7 us of launch latency to a 20 us kernel)
     barrier()
-    for _ in range(min(args.steps, 4096)):
-        mppi.enqueue(pose)
-    mppi.wait()
-    k_ms, k_n = mppi.kernelTime()
-    mppi.setKernelTiming(False)
+    n_k = min(args.steps, 4096)
+    k_ms = mppi.timeRollout(pose, n_k)
+    k_n = n_k
     clocks = sampler.stop()
     barrier()
 
@@ -386,7 +384,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24,
                     "d2h_bytes_per_step": 16,
-                    "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command read back from pinned memory"},
+                    "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the update kernel into mapped pinned memory"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "mppi_rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,

@@ -115,6 +115,10 @@ int b2n_mppi_set_state_ring(b2n_mppi *h, int n);
 int b2n_mppi_launch_count(const b2n_mppi *h, uint64_t *launches);
 int b2n_mppi_set_kernel_timing(b2n_mppi *h, int on);
 int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples);
+/* bench hook: the rollout kernel alone, `launches` times back to back on the handle's stream between two CUDA events
+ * (same arguments as the last call would use, state tensor rotating through the ring; the plan is not updated);
+ * avg_ms = elapsed / launches */
+int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int launches, double *avg_ms);
 
 /* Sharded operation: every rank simulates its slice of the rollouts, the [T][6]
  * partials are exchanged with ONE ncclAllGather, every rank applies the identical update.

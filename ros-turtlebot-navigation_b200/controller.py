@@ -140,6 +140,12 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def timeRollout(self, ps, launches):
+        """bench hook: average duration (ms) of the rollout kernel over `launches` back-to-back launches"""
+        ms = C.c_double()
+        _capi.check(self._lib.b2n_mppi_time_rollout(self._h, ps.x, ps.y, ps.theta, int(launches), C.byref(ms)))
+        return ms.value
+
     def commInit(self, rank, nranks, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _capi.check(self._lib.b2n_mppi_comm_init(self._h, rank, nranks, buf))

@@ -39,7 +39,10 @@ struct b2n_mppi
   double *d_gathered = nullptr;          // [nranks][T][6]
   double *d_out = nullptr;               // [2]
   double *d_stepstats = nullptr;         // [T][2]
-  double *h_out = nullptr;               // pinned [2]
+  double *h_out = nullptr;               // pinned, mapped [2]: the update kernel writes the controls here
+  double *d_out_host = nullptr;          // device view of h_out
+  bool use_pdl = false;                  // programmatic dependent launch of the update kernel: measured 2.4 us per call SLOWER at
+                                         // K = 16384 (the early-scheduled update CTAs take residency from the rollout grid); B2N_MPPI_PDL=1 turns it on
   double *d_ext = nullptr;               // [K][T][2]
   bool ext_armed = false;
   int capture = 0;
@@ -136,7 +139,8 @@ int set_device(const b2n_mppi *h)
   return B2N_OK;
 }
 
-int enqueue_call(b2n_mppi *h, double x, double y, double theta)
+// kernel arguments of one call (the state-tensor slot is chosen by the caller)
+MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
 {
   const b2n_mppi_params &p = h->p;
   MppiArgs a;
@@ -160,10 +164,43 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   a.obs_ymax = h->obs_ymin + h->obs_ysize * h->obs_res;
   a.obs_weight = h->obs_weight; a.obs_d0 = h->obs_d0; a.obs_off = h->obs_off; a.obs_dist = h->d_obs;
   a.u_plan = h->d_u[h->cur];
+  a.ext = h->d_ext; a.J_out = h->d_J; a.du_out = h->d_du; a.partials = h->d_partials;
+  return a;
+}
+
+// the FAST variant needs: own noise, no taps, no obstacle term, a full last lane, TMA stores, and every half-step
+// heading increment inside the Taylor range of mppi_sincos_small: |h w / 2| <= c_w (|uL| + |uR|) / 2 with
+// |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
+bool fast_variant(const b2n_mppi *h, const MppiArgs &a)
+{
+  const double u_bound = 2.0 * h->plan_abs_max + 5.78 * (a.sigL + a.sigR);
+  return !a.external_noise && !a.capture && !a.obs_on && a.tma_store && h->T == h->S * h->G &&
+         0.5 * std::fabs(a.c_w) * u_bound <= 0.125 && !h->force_generic;
+}
+
+// update kernel behind the rollout kernel with programmatic dependent launch: its CTAs may be scheduled while the
+// rollout grid drains and block in cudaGridDependencySynchronize() until the partials are complete and visible
+int launch_update(b2n_mppi *h, const MppiUpdateArgs &u)
+{
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)h->T); cfg.blockDim = dim3(kMppiUpdateThreads); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
+  B2N_CUDA(cudaLaunchKernelEx(&cfg, mppi_update_kernel, u));
+  h->launches++;
+  return B2N_OK;
+}
+
+int enqueue_call(b2n_mppi *h, double x, double y, double theta)
+{
+  const b2n_mppi_params &p = h->p;
+  MppiArgs a = make_args(h, x, y, theta);
   h->last_slot = h->ring_pos;
   a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
   h->ring_pos = (h->ring_pos + 1) % h->ring;
-  a.ext = h->d_ext; a.J_out = h->d_J; a.du_out = h->d_du; a.partials = h->d_partials;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->ev_used + 2 <= h->ev.size()) {
@@ -171,13 +208,7 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
     h->ev_used += 2;
     B2N_CUDA(cudaEventRecord(e0, h->stream));
   }
-  // the FAST variant needs: own noise, no taps, no obstacle term, a full last lane, TMA stores, and every half-step
-  // heading increment inside the Taylor range of mppi_sincos_small: |h w / 2| <= c_w (|uL| + |uR|) / 2 with
-  // |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
-  const double u_bound = 2.0 * h->plan_abs_max + 5.78 * (a.sigL + a.sigR);
-  const bool fast = !a.external_noise && !a.capture && !a.obs_on && a.tma_store && h->T == h->S * h->G &&
-                    0.5 * std::fabs(a.c_w) * u_bound <= 0.125 && !h->force_generic;
-  launch_rollout(h, a, fast);
+  launch_rollout(h, a, fast_variant(h, a));
   B2N_CUDA(cudaGetLastError());
   if (e1) B2N_CUDA(cudaEventRecord(e1, h->stream));
   h->launches++;
@@ -191,25 +222,20 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   u.uinit[0] = h->uinit[0]; u.uinit[1] = h->uinit[1];
   u.u_cur = h->d_u[h->cur];
   u.u_next = h->d_u[h->cur ^ 1];
-  u.out = h->d_out;
+  u.out = h->d_out_host;               // mapped pinned memory: the controls land on the host without a copy operation
   u.stepstats = h->d_stepstats;
   u.merged = h->d_merged;
   if (h->nranks > 1) {
     // local merge -> one allgather of [T][6] doubles -> identical update on every rank
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 1;
-    mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
-    B2N_CUDA(cudaGetLastError());
-    h->launches++;
+    if (int rc = launch_update(h, u)) return rc;
     ncclResult_t r = ncclAllGather(h->d_merged, h->d_gathered, (size_t)h->T * 6, ncclDouble, h->comm, h->stream);
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
     u.partials = h->d_gathered; u.n_partials = h->nranks; u.merge_only = 0;
   } else {
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
   }
-  mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
-  B2N_CUDA(cudaGetLastError());
-  h->launches++;
-  B2N_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = launch_update(h, u)) return rc;
 
   h->cur ^= 1;
   h->call++;
@@ -286,7 +312,9 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_TRY(cudaMalloc(&h->d_merged, (size_t)T * 6 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_out, 2 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_stepstats, (size_t)T * 2 * sizeof(double)));
-  B2N_TRY(cudaMallocHost(&h->h_out, 2 * sizeof(double)));
+  B2N_TRY(cudaHostAlloc(&h->h_out, 2 * sizeof(double), cudaHostAllocMapped));
+  B2N_TRY(cudaHostGetDevicePointer(&h->d_out_host, h->h_out, 0));
+  if (const char *env = std::getenv("B2N_MPPI_PDL")) h->use_pdl = env[0] == '1';
   B2N_TRY(cudaStreamSynchronize(h->stream));
 #undef B2N_TRY
   *out = h;
@@ -465,9 +493,7 @@ int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count)
   std::memset(&u, 0, sizeof(u));
   u.T = h->T; u.inv_lambda = 1.0 / h->p.lambda; u.partials = h->d_partials; u.n_partials = h->grid;
   u.merge_only = 1; u.merged = h->d_merged;
-  mppi_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u);
-  B2N_CUDA(cudaGetLastError());
-  h->launches++;
+  if (int rc = launch_update(h, u)) return rc;
   return copy_out(h, out, h->d_merged, count * sizeof(double));
 }
 
@@ -543,6 +569,33 @@ int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples)
   *avg_ms = n ? total / n : 0.0;
   *samples = n;
   h->ev_used = 0;
+  return B2N_OK;
+}
+
+int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int launches, double *avg_ms)
+{
+  B2N_REQUIRE(h && avg_ms && launches > 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  MppiArgs a = make_args(h, x, y, theta);
+  const bool fast = fast_variant(h, a);
+  cudaEvent_t e0, e1;
+  B2N_CUDA(cudaEventCreate(&e0));
+  B2N_CUDA(cudaEventCreate(&e1));
+  B2N_CUDA(cudaEventRecord(e0, h->stream));
+  for (int i = 0; i < launches; i++) {
+    a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
+    h->ring_pos = (h->ring_pos + 1) % h->ring;
+    a.call = h->call + (uint32_t)i;
+    launch_rollout(h, a, fast);
+  }
+  B2N_CUDA(cudaGetLastError());
+  B2N_CUDA(cudaEventRecord(e1, h->stream));
+  B2N_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B2N_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->launches += (uint64_t)launches;
+  *avg_ms = (double)ms / launches;
   return B2N_OK;
 }
 

@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kMppiThreads, (S >= 8 ? 1 : (S >= 4 ? 3 : 4)))
   double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
   double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4);             // [warps][TP][6] (epilogue)
 
+  // let a programmatically dependent grid (the update kernel) be scheduled as soon as this grid frees resources;
+  // it blocks in griddepcontrol.wait until this grid has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = lane & (G - 1);    // position inside the rollout's lane group
@@ -393,6 +396,9 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   const int T = a.T;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
 
+  // launched with programmatic stream serialization: wait here until the producing grid has finished and its
+  // partials are visible (a no-op for an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // phase 1: the step's minimum over all partials
   double m = inf;
   for (int p = threadIdx.x; p < a.n_partials; p += kMppiUpdateThreads) m = fmin(m, a.partials[((size_t)p * T + t) * 6]);

@@ -42,6 +42,8 @@ struct b2n_pf
   unsigned long long *d_spill = nullptr, *d_stats = nullptr;
   // distance-field launch shape (configure_df): one CTA per SM, df_warps particles in flight per CTA
   int df_grid = 0, df_warps = 1, df_hcap = 0, df_hcap_request = 0, df_gcap = 0, df_cols = 0;
+  int df_gl_active = 32;
+  int df_gl = 16;                     // lanes per particle in the distance-field kernel: 32 (one particle per warp), 16 or 8
   bool df_tmem = true, df_tmem_active = true;
   size_t df_smem = 0, spill_entries = 0;
   size_t smem_optin = 0;
@@ -150,10 +152,40 @@ int upload_scan(b2n_pf *h, const float *scan, int n_beams)
 int configure_df(b2n_pf *h)
 {
   const PfConst &c = h->c;
-  int W = std::max(1, std::min(kDfMaxWarps, (h->N + h->n_sm - 1) / h->n_sm));
   const int words = (c.G + 31) / 32;
   const int cols_needed = (words + 31) / 32 + 1;
   const size_t budget = h->smem_optin - 2048;     // static shared memory and alignment slack
+  const int per_sm = std::max(1, std::min(kDfMaxWarps, (h->N + h->n_sm - 1) / h->n_sm));   // particles in flight per SM
+  int gl = h->df_tmem ? h->df_gl : 32;
+  if (gl != 32) {
+    // several particles per warp (rbpf_distance_field_groups_kernel)
+    const int ng = 32 / gl;
+    const int W = (per_sm + ng - 1) / ng;
+    const int cols_per_warp = ng * cols_needed;
+    int hcap = 0;
+    const size_t stage_bytes = (size_t)W * ng * 64 * 4;
+    if (((W + 3) / 4) * cols_per_warp <= 512 && budget > stage_bytes + 1024) {
+      hcap = (int)((budget - stage_bytes) / ((size_t)W * ng) / 8) - 2;
+      hcap = std::min(hcap & ~1, 16384);
+    }
+    if (hcap >= 64) {
+      if (h->df_hcap_request > 0) hcap = std::min(hcap, h->df_hcap_request);
+      h->df_warps = W; h->df_hcap = hcap; h->df_cols = cols_per_warp; h->df_gl_active = gl;
+      h->df_grid = std::max(1, std::min(h->n_sm, (h->N + W * ng - 1) / (W * ng)));
+      h->df_gcap = std::min(c.G, 16384);
+      h->df_smem = pf_dfg_smem_bytes(hcap, W, ng);
+      h->df_tmem_active = true;
+      const size_t need = (size_t)h->df_grid * W * ng * h->df_gcap;
+      if (need > h->spill_entries) {
+        cudaFree(h->d_spill); h->d_spill = nullptr; h->spill_entries = 0;
+        B2N_CUDA(cudaMalloc(&h->d_spill, need * sizeof(unsigned long long)));
+        h->spill_entries = need;
+      }
+      return B2N_OK;
+    }
+  }
+  // one particle per warp (rbpf_distance_field_kernel)
+  int W = per_sm;
   bool tmem = h->df_tmem;
   int hcap = 0, cols = 0;
   for (;; W--) {
@@ -167,18 +199,17 @@ int configure_df(b2n_pf *h)
   }
   B2N_REQUIRE(hcap >= 2, B2N_ERR_UNSUPPORTED, "the distance-field kernel does not fit this map in shared memory");
   if (h->df_hcap_request > 0) hcap = std::min(hcap, h->df_hcap_request);
-  h->df_warps = W; h->df_hcap = hcap; h->df_cols = cols;
+  h->df_warps = W; h->df_hcap = hcap; h->df_cols = cols; h->df_gl_active = 32;
   h->df_grid = std::max(1, std::min(h->n_sm, (h->N + W - 1) / W));
   h->df_gcap = std::min(c.G, 16384);
   h->df_smem = pf_df_smem_bytes(c.G, hcap, W, tmem);
-  const bool tmem_used = tmem;
+  h->df_tmem_active = tmem;
   const size_t need = (size_t)h->df_grid * W * h->df_gcap;
   if (need > h->spill_entries) {
     cudaFree(h->d_spill); h->d_spill = nullptr; h->spill_entries = 0;
     B2N_CUDA(cudaMalloc(&h->d_spill, need * sizeof(unsigned long long)));
     h->spill_entries = need;
   }
-  h->df_tmem_active = tmem_used;
   return B2N_OK;
 }
 
@@ -370,7 +401,10 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
   // the limit is per function and process-wide: always the device maximum, never lowered by another handle
   B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
   B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
+  B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_groups_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
+  B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_groups_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
   if (const char *env = std::getenv("B2N_PF_DF_SMEM_MARKS")) h->df_tmem = env[0] != '1';
+  if (const char *env = std::getenv("B2N_PF_DF_LANES")) { const int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) h->df_gl = v; }
   if (configure_df(h) != B2N_OK) { b2n_pf_destroy(h); return B2N_ERR_CUDA; }
   if (pf_smem_bytes(h->max_beams, c.pz_stage, kPfWarpsPerCta) > prop.sharedMemPerBlockOptin) {
     set_error("max_beams = %d needs more shared memory than the device has", h->max_beams);
@@ -467,7 +501,9 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
     PfDfArgs d;
     d.hcap = h->df_hcap; d.gcap = h->df_gcap; d.warps = h->df_warps; d.cols_per_warp = h->df_cols;
     d.spill = h->d_spill; d.stats = h->d_stats; d.status = h->d_status;
-    if (h->df_tmem_active) rbpf_distance_field_kernel<true><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
+    if (h->df_gl_active == 8) rbpf_distance_field_groups_kernel<8><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
+    else if (h->df_gl_active == 16) rbpf_distance_field_groups_kernel<16><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
+    else if (h->df_tmem_active) rbpf_distance_field_kernel<true><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
     else rbpf_distance_field_kernel<false><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
   }
   B2N_CUDA(cudaGetLastError());

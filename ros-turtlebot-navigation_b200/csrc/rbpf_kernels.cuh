@@ -672,33 +672,40 @@ struct HeapDev
     return hole == 0;
   }
   __device__ __forceinline__ void push_any(uint2 e) { sift_up(len, e); len++; }
-  // std::pop_heap + pop_back = __adjust_heap(first, 0, len - 1, last value), len >= 2, whole heap in shared memory
+  // std::pop_heap + pop_back = __adjust_heap(first, 0, len - 1, last value), len >= 2, whole heap in shared memory.
+  // The walk is carried on byte addresses: a = address of slot `second` (= entry second - 1); its children pair
+  // (entries 2 second + 1, 2 second + 2) sits in slots 2 second + 2, 2 second + 3 = address 2 a - (sb - 16).
   __device__ __forceinline__ void pop_shared()
   {
     const int L = --len;                                   // index of the last entry, >= 1
     const uint2 value = lds64(sb + 8u * (uint32_t)(L + 1));
-    const int limit = (L - 1) >> 1;
-    int second = 0;
-    uint32_t hole_addr = sb + 8u;
+    const uint32_t alim = sb + 8u * (uint32_t)((L - 1) >> 1);
+    const uint32_t K = sb - 16u;
+    uint32_t a = sb;                                       // slot of index `second` = 0 ... the hole is entry `second`
     uint2 above = make_uint2(0u, 0u);                      // the entry now sitting in the hole's parent
-    while (second < limit) {
-      second = 2 * second + 2;
-      const uint4 pr = lds128(sb + 8u * (uint32_t)second);            // entries second - 1 (x, y) and second (z, w)
-      const bool left = pr.w > pr.y;                                  // comp(right, left): take the left child
-      above = left ? make_uint2(pr.x, pr.y) : make_uint2(pr.z, pr.w);
-      second -= left ? 1 : 0;
-      sts64(hole_addr, above);
-      hole_addr = sb + 8u * (uint32_t)(second + 1);
+    // (loading the children pairs of both candidates one level ahead was tried: more shared-memory wavefronts and
+    // issue slots than the latency it hides - measured slower in every lane-group configuration)
+    while (a < alim) {
+      const uint32_t hole_a = a + 8u;
+      a = 2u * a - K;
+      const uint4 pr = lds128(a);                          // entries second - 1 (x, y) and second (z, w)
+      const bool left = pr.w > pr.y;                       // comp(right, left): take the left child
+      above.x = left ? pr.x : pr.z;
+      above.y = min(pr.y, pr.w);
+      a -= left ? 8u : 0u;
+      sts64(hole_a, above);
     }
+    int second = (int)((a - sb) >> 3);
     if ((L & 1) == 0 && second == ((L - 2) >> 1)) {
-      second = 2 * second + 1;                                        // the only child, entry 2 (second + 1) - 1
-      above = lds64(sb + 8u * (uint32_t)(second + 1));
-      sts64(hole_addr, above);
-      hole_addr = sb + 8u * (uint32_t)(second + 1);
+      const uint32_t hole_a = a + 8u;
+      second = 2 * second + 1;                             // the only child
+      a = sb + 8u * (uint32_t)second;
+      above = lds64(a + 8u);
+      sts64(hole_a, above);
     }
     // __push_heap from the leaf: the parent of the hole is the entry just moved there
     if (second > 0 && above.y > value.y) sift_up(second, value);
-    else sts64(hole_addr, value);
+    else sts64(a + 8u, value);
   }
   __device__ __forceinline__ void pop_any()
   {
@@ -871,6 +878,175 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_kerne
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_slot), "n"(512));
   }
+}
+
+// ---- the same brushfire with SEVERAL particles per warp -------------------------------------------------------------
+// The single-particle-per-warp kernel above is bound by instruction issue: 28 warps per SM each spend ~250 issue
+// slots per heap step on work that only one lane's worth of data needs.  Here a warp carries NG = 32 / GL particles,
+// one per group of GL lanes (8 or 16): the groups run their heap loops under SIMT divergence (different trip counts
+// are masked, the common iterations issue once for all groups), so an issue slot serves up to NG particles, and the
+// 28 chains of an SM need only 28 / NG warps.  The visited bitmaps stay in tensor memory; tcgen05.ld/st are warp-wide
+// with a uniform address, so the two columns a group needs are staged through a small shared-memory window
+// ([NG][2][32] words per warp): one tcgen05.ld per group, testers read and atomicOr their word there, dirty
+// windows go back with one tcgen05.st.
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
+{
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  return r;
+}
+
+__host__ __device__ inline size_t pf_dfg_smem_bytes(int hcap, int warps, int ng)
+{
+  return (size_t)warps * ng * (size_t)(hcap + 2) * 8 + (size_t)warps * ng * 64 * 4;
+}
+
+template <int GL>
+__global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_groups_kernel(const __grid_constant__ PfConst c, const PfPlanes pl,
+                                                                                          const PfDfArgs d)
+{
+  constexpr int NG = 32 / GL;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t tmem_base_slot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane / GL, sl = lane % GL;
+  const unsigned gmask = ((GL == 32) ? 0xFFFFFFFFu : ((1u << GL) - 1u)) << (q * GL);
+  const int slots = d.warps * NG, slot = warp * NG + q;
+  const int words = (c.G + 31) / 32, cols = (words + 31) / 32;
+  const int CG = cols + 1;                                               // TMEM columns per particle (one spare for the x2 loads)
+  const int xs = c.xsize, ys = c.ysize, R = c.cell_radius;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t twarp = tmem_base_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * d.cols_per_warp);
+
+  HeapDev H;
+  H.sb = smem_u32(smem) + (uint32_t)slot * (uint32_t)(d.hcap + 2) * 8u;
+  H.g = reinterpret_cast<uint2 *>(d.spill) + ((size_t)blockIdx.x * slots + slot) * d.gcap;
+  H.hcap = d.hcap; H.gcap = d.gcap; H.overflow = false; H.len = 0;
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + (size_t)slots * (d.hcap + 2) * 8) + (size_t)warp * NG * 64;   // [NG][2][32]
+  uint32_t *my_stage = stage + q * 64;
+  unsigned long long iters = 0;
+  int heap_max = 0;
+  // lanes 0..3 of a group test (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
+  const int dI = sl == 0 ? -1 : sl == 2 ? 1 : 0, dJ = sl == 1 ? -1 : sl == 3 ? 1 : 0;
+  const int dIdx = dI * xs + dJ;
+  const uint32_t dEntry = ((uint32_t)dI << 24) + ((uint32_t)dJ << 16);
+  const bool tester = sl < 4;
+  const int R2 = R * R;
+
+  for (int p0 = blockIdx.x * slots; p0 < c.N; p0 += gridDim.x * slots) {
+    const int p = p0 + slot;
+    const bool act = p < c.N && pl.meta[min(p, c.N - 1)].n_occ != 0;     // grid_mapper.cpp:335-338
+    const uint16_t *nxt = pl.nxt + (size_t)min(p, c.N - 1) * c.nxt_stride;
+    uint32_t *d2p = pl.d2 + (size_t)min(p, c.N - 1) * c.gstride;
+    uint32_t *d2n = d2p + dIdx;
+    for (int col = 0; col < NG * CG; col++) tmem_st1(twarp + col, 0u);
+    tmem_wait_st();
+    H.len = 0;
+    // seeds in the iteration order of occ_cells_ (:348-361), the groups in lockstep; all of distance 0, so push_heap
+    // leaves them where they land
+    {
+      uint32_t key = act ? (uint32_t)nxt[c.G] : (uint32_t)kNil16;
+      while (__any_sync(kFullMask, key != kNil16)) {
+        const bool has = key != kNil16;
+        if (has) {
+          const uint32_t ki = key / (uint32_t)xs, kj = key - ki * (uint32_t)xs;
+          if (sl == 0) d2p[key] = 0;
+          H.set(H.len, make_uint2((ki << 24) | (kj << 16) | (ki << 8) | kj, 0u));
+          H.len++;
+        }
+#pragma unroll
+        for (int qq = 0; qq < NG; qq++) {
+          const uint32_t kq = __shfl_sync(kFullMask, has ? key : 0xFFFFFFFFu, qq * GL);
+          if (kq != 0xFFFFFFFFu) {
+            const uint32_t ta = twarp + (uint32_t)(qq * CG) + (kq >> 10);
+            uint32_t v = tmem_ld1(ta);
+            if ((uint32_t)lane == ((kq >> 5) & 31u)) v |= 1u << (kq & 31u);
+            tmem_st1(ta, v);
+            tmem_wait_st();
+          }
+        }
+        if (has) key = nxt[key];
+      }
+    }
+    heap_max = max(heap_max, H.len);
+    uint32_t it = 0;
+    while (__any_sync(kFullMask, H.len > 0)) {
+      const bool on = H.len > 0;
+      const uint2 top = lds64(H.sb + 8u);                                 // Q.top(), :399
+      const int ci = (int)(top.x >> 24), cj = (int)((top.x >> 16) & 0xFFu), si = (int)((top.x >> 8) & 0xFFu), sj = (int)(top.x & 0xFFu);
+      const int ni = ci + dI, nj = cj + dJ;
+      const bool inb = on && tester && (unsigned)ni < (unsigned)xs && (unsigned)nj < (unsigned)ys;
+      const int idx0 = ci * xs + cj;                                      // grid2RowMajor
+      const int idx = inb ? idx0 + dIdx : idx0;
+      const uint32_t colA = on ? ((uint32_t)max(idx0 - xs, 0) >> 10) : 0u;   // columns colA, colA + 1 hold all four neighbours
+      uint32_t cA[NG], a0[NG], a1[NG];
+#pragma unroll
+      for (int qq = 0; qq < NG; qq++) {
+        cA[qq] = __shfl_sync(kFullMask, colA, qq * GL);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(a0[qq]), "=r"(a1[qq]) : "r"(twarp + (uint32_t)(qq * CG) + cA[qq]));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");      // one wait for all the groups' loads
+#pragma unroll
+      for (int qq = 0; qq < NG; qq++) {
+        stage[qq * 64 + lane] = a0[qq];
+        stage[qq * 64 + 32 + lane] = a1[qq];
+      }
+      __syncwarp();
+      const uint32_t w = (uint32_t)idx >> 5;
+      uint32_t *wp = my_stage + (((w >> 5) != colA) ? 32 : 0) + (w & 31u);
+      const uint32_t word = *wp;
+      const int di = ni - si, dj = nj - sj;
+      const int d2 = di * di + dj * dj;
+      // unmarked, inside distances_.at()'s range, not farther than cell_radius_
+      const bool valid = inb && !((word >> (idx & 31)) & 1u) && d2 <= R2 && max(abs(di), abs(dj)) < R;
+      if (valid) {
+        d2n[idx0] = (uint32_t)d2;
+        atomicOr(wp, 1u << (idx & 31));
+      }
+      const uint2 entry = make_uint2(top.x + dEntry, (uint32_t)d2);
+      const unsigned vmask = __ballot_sync(kFullMask, valid);
+      if (vmask) {
+        __syncwarp();
+#pragma unroll
+        for (int qq = 0; qq < NG; qq++) {
+          if ((vmask >> (qq * GL)) & 0xFu) tmem_st2(twarp + (uint32_t)(qq * CG) + cA[qq], stage[qq * 64 + lane], stage[qq * 64 + 32 + lane]);
+        }
+        tmem_wait_st();
+      }
+      unsigned m = (vmask >> (q * GL)) & 0xFu;
+      if (m) {
+        const bool shared_ok = H.len + 4 <= H.hcap;
+        do {
+          const int from = q * GL + __ffs(m) - 1;
+          m &= m - 1;
+          const uint2 e = make_uint2(__shfl_sync(gmask, entry.x, from), __shfl_sync(gmask, entry.y, from));
+          if (shared_ok) H.push_shared(e);
+          else H.push_any(e);
+        } while (m);
+        heap_max = max(heap_max, H.len);
+      }
+      // Q.pop() pops whatever is on top NOW (a pushed cell may be nearer than the current top), :431
+      if (on) {
+        if (H.len >= 2 && H.len <= H.hcap) H.pop_shared();
+        else H.pop_any();
+        it++;
+      }
+    }
+    iters += it;
+  }
+  if (d.stats && sl == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); }
+  if (H.overflow && sl == 0) atomicOr(d.status, kDfStatusHeapOverflow);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_slot), "n"(512));
 }
 
 // ---- normalise, N_eff, low-variance walk (particle_filter.cpp:442-500) -----------------------------------------------
