@@ -198,6 +198,10 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
     achieved = RBPF_N * RBPF_DF_BYTES_PER_PARTICLE / (df_ms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("rbpf_distance_field_kernel_dram_bytes_per_launch")
     out = {
         "metric": "rbpf_particle_updates_per_sec", "unit": "particle-updates/s",
         "value": RBPF_N * n_scans / (dev_ms * 1e-3),
@@ -212,8 +216,8 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
                 "h2d_bytes_per_step": 4 * RBPF_BEAMS + 72, "d2h_bytes_per_step": 16,
                 "note": "synchronous SLAM(): host scan + twist + odometry in, status / N_eff / resample flag out"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "rbpf_distance_field_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel_ms": df_ms,
+        "roofline": {"bound": "hbm", "kernel": "rbpf_distance_field_groups_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel_ms": df_ms,
                      "algorithmic_bytes_per_launch": RBPF_N * RBPF_DF_BYTES_PER_PARTICLE,
                      "note": "the reference's brushfire is order-dependent (heap ties, seed order): serial per particle by definition, "
                              "parallel over particles only - latency bound, not HBM bound (DESIGN.md 4.3)"},
