@@ -58,3 +58,53 @@ def test_mppi_cpp_equals_ctypes_path(bindir, gpu_pkg):
     for c in range(3):
         v = m.newControls(gpu_pkg.Pose(theta=0.0, x=0.0, y=0.0))
         assert (v.ul, v.ur) == got[c]
+
+
+# ------------------------------------------------------------------------------- bmapping surface ---
+def test_slam_surface_compiles_and_links(bindir, pkg):
+    exe = _compile("slam_node_like.cpp", str(bindir / "slam_node_like"))
+    r = subprocess.run([exe], input="0 0\n", capture_output=True, text=True)
+    if pkg.load_library().b2n_device_count() < 1:
+        assert r.returncode == 3 and r.stdout.startswith("NO_DEVICE"), (r.returncode, r.stdout, r.stderr)
+    else:
+        assert r.returncode == 0, (r.stdout, r.stderr)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RIGID2D), reason="reference tree not present on this machine")
+def test_slam_surface_compiles_against_reference_rigid2d(bindir):
+    """The catkin situation: the reference's rigid2d headers (real Transform2D / Twist2D / Pose) come first."""
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + REF_RIGID2D, "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "slam_node_like.cpp"), "/root/reference/rigid2d/src/rigid2d/rigid2d.cpp",
+           "-o", str(bindir / "slam_node_like_ref"), "-L" + LIBDIR, "-lb2nav", "-Wl,-rpath," + LIBDIR]
+    subprocess.run(cmd, check=True)
+
+
+@pytest.mark.gpu
+def test_slam_cpp_equals_ctypes_path(bindir, gpu_pkg):
+    """bmapping::ParticleFilter through the C++ header and through the ctypes mirror: same robot state, same map."""
+    import numpy as np
+    import _oracle as orc
+    exe = _compile("slam_node_like.cpp", str(bindir / "slam_node_like_gpu"))
+    n_scans, N = 4, 8
+    poses, twists = orc.circle_path(n_scans)
+    rng = np.random.default_rng(11)
+    scans = [orc.room_scan(poses[i + 1], rng=rng) for i in range(n_scans)]
+    lines = ["%d %d" % (n_scans, 360)]
+    for i in range(n_scans):
+        lines.append(" ".join(repr(float(v)) for v in (*twists[i], *poses[i + 1], *poses[i])))
+        lines.append(" ".join(repr(float(v)) for v in scans[i]))
+    th0, x0, y0 = poses[0]
+    r = subprocess.run([exe, str(N), "1", repr(float(x0)), repr(float(y0)), repr(float(th0))], input="\n".join(lines) + "\n",
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    got = [ln.split() for ln in r.stdout.strip().splitlines()]
+    f = gpu_pkg.bmapping.make_filter(orc.pf_params(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3),
+                                                   sample_range=(1e-3, 1e-3, 1e-3), srr=0.001, srt=0.001, str_=0.001, stt=0.001,
+                                                   beam_max=6.28319, beam_delta=0.0174533))
+    f.seed(1)
+    for i in range(n_scans):
+        f.SLAM(scans[i], gpu_pkg.Twist2D(*twists[i]), gpu_pkg.Pose(*poses[i + 1]), gpu_pkg.Pose(*poses[i]))
+        m = f.newMap().astype(np.int64)
+        th, x, y = f.getRobotState().displacement()
+        assert (float(got[i][0]), float(got[i][1]), float(got[i][2])) == (th, x, y)
+        assert int(got[i][3]) == int(np.sum((np.arange(m.size) % 977 + 1) * m)) and int(got[i][4]) == m.size
