@@ -215,6 +215,17 @@ int b2n_pf_set_heap_capacity(b2n_pf *h, int entries);
 int b2n_pf_host_tables(const b2n_pf_params *params, double constants[4], double *beam_cs, size_t beam_count, double *pz,
                        size_t pz_cap, int *pz_n);
 int b2n_pf_comm_init(b2n_pf *h, int rank, int nranks, const void *unique_id128);
+/* Resampling across ranks.  Every rank runs the identical walk on the allgathered weights and so holds
+ * the same ancestor vector; b2n_pf_slam then moves particles whose ancestor lives on another GPU with one group of
+ * ncclSend/ncclRecv (each migrating particle once per destination rank) and copies the rest on the device.
+ * b2n_pf_plan_migration is the pure host part, exposed for CPU tests: for `rank`, copy1[n_local] = local source index
+ * in the old set or -1; copy2[n_local] = local slot of the new set to copy from after the exchange or -1;
+ * recv = (local slot, global ancestor, source rank) triples; send = (local particle, destination rank) pairs, both in
+ * the order the exchange posts them (ascending ancestor per peer). */
+int b2n_pf_plan_migration(const int32_t *ancestors, int n_total, int rank, int nranks, int32_t *copy1, int32_t *copy2, int32_t *recv,
+                          size_t recv_cap, int *n_recv, int32_t *send, size_t send_cap, int *n_send);
+/* particles received from / sent to other ranks by the last SLAM() */
+int b2n_pf_get_migration(const b2n_pf *h, int *received, int *sent);
 
 #ifdef __cplusplus
 }

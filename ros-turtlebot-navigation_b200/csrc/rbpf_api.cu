@@ -50,6 +50,8 @@ struct b2n_pf
   double *d_best = nullptr, *h_best = nullptr;   // pose[3], weight
   int8_t *d_map = nullptr;
   double *d_lik = nullptr;
+  int32_t *d_idx = nullptr;           // [2][N] copy lists of a cross-rank resampling
+  int last_migrated_in = 0, last_migrated_out = 0;
 
   uint64_t seed = 0;
   uint32_t call = 0;
@@ -143,6 +145,53 @@ int upload_scan(b2n_pf *h, const float *scan, int n_beams)
   std::memcpy(h->h_scan, scan, sizeof(float) * n_beams);
   B2N_CUDA(cudaMemcpyAsync(h->d_scan, h->h_scan, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
   return B2N_OK;
+}
+
+// Where every slot of THIS rank takes its particle from after a resampling that every rank computed identically
+// (SURVEY.md 8e): local ancestors are copied on the device; an ancestor living on another rank is received ONCE per
+// (ancestor, destination rank) into the first slot that wants it and fanned out from there; symmetric send list.
+// Order of the exchange for a pair (s -> t): ascending global ancestor index - both sides derive it from the same
+// ancestor vector, so sends and receives match without any negotiation.
+struct MigrationPlan
+{
+  std::vector<int32_t> copy1;       // [n_local] local source index in the OLD set, -1 = not a local copy
+  std::vector<int32_t> copy2;       // [n_local] local slot in the NEW set to copy from (second pass), -1 = none
+  std::vector<int32_t> recv_slot, recv_anc, recv_rank;   // receive into local slot <- global ancestor on rank
+  std::vector<int32_t> send_idx, send_rank;              // send local particle index -> rank
+};
+
+void plan_migration(const int32_t *anc, int n_total, int n_local, int rank, int nranks, MigrationPlan &pl)
+{
+  pl.copy1.assign(n_local, -1); pl.copy2.assign(n_local, -1);
+  pl.recv_slot.clear(); pl.recv_anc.clear(); pl.recv_rank.clear(); pl.send_idx.clear(); pl.send_rank.clear();
+  const int off = rank * n_local;
+  // receives: my slots whose ancestor is remote; ancestors are non-decreasing in m (low-variance walk), so equal
+  // ancestors are adjacent, but do not rely on it: remember the first slot per remote ancestor
+  std::vector<int32_t> first_slot(n_total, -1);
+  for (int m = 0; m < n_local; m++) {
+    const int a = anc[off + m];
+    const int s = a / n_local;
+    if (s == rank) { pl.copy1[m] = a - off; continue; }
+    if (first_slot[a] < 0) first_slot[a] = m;
+    else pl.copy2[m] = first_slot[a];
+  }
+  for (int s = 0; s < nranks; s++) {
+    if (s == rank) continue;
+    for (int a = s * n_local; a < (s + 1) * n_local; a++)
+      if (first_slot[a] >= 0) { pl.recv_slot.push_back(first_slot[a]); pl.recv_anc.push_back(a); pl.recv_rank.push_back(s); }
+  }
+  // sends: for every other rank t, my particles that some slot of t wants, ascending
+  std::vector<char> wanted(n_local);
+  for (int t = 0; t < nranks; t++) {
+    if (t == rank) continue;
+    std::fill(wanted.begin(), wanted.end(), 0);
+    for (int m = t * n_local; m < (t + 1) * n_local; m++) {
+      const int a = anc[m];
+      if (a / n_local == rank) wanted[a - off] = 1;
+    }
+    for (int i = 0; i < n_local; i++)
+      if (wanted[i]) { pl.send_idx.push_back(i); pl.send_rank.push_back(t); }
+  }
 }
 
 // Launch shape of the distance-field kernel (rbpf_kernels.cuh): one CTA per SM, one particle per warp, as many warps
@@ -296,6 +345,58 @@ void host_tables(const b2n_pf_params &p, int xsize, int ysize, long long G, int 
 
 }
 
+// Resampling across ranks: device copies for local ancestors, one ncclSend/ncclRecv group for the particles that
+// change GPU (five contiguous pieces each: log-odds, squared distances, occupied-set links, bucket heads, meta), then a
+// second device pass fans received particles out to the other slots that chose the same ancestor.
+int migrate_particles(b2n_pf *h, const PfPlanes &src, const PfPlanes &dst)
+{
+  const PfConst &c = h->c;
+  MigrationPlan mp;
+  plan_migration(h->h_anc.data(), h->n_total, h->N, h->rank, h->nranks, mp);
+  if (!h->d_idx) B2N_CUDA(cudaMalloc(&h->d_idx, sizeof(int32_t) * 2 * (size_t)h->N));
+  B2N_CUDA(cudaMemcpyAsync(h->d_idx, mp.copy1.data(), sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream));
+  B2N_CUDA(cudaMemcpyAsync(h->d_idx + h->N, mp.copy2.data(), sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream));
+  dim3 grid(8, h->N);
+  rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, src, dst, h->d_idx);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  const size_t n_send = mp.send_idx.size(), n_recv = mp.recv_slot.size();
+  h->last_migrated_in = (int)n_recv; h->last_migrated_out = (int)n_send;
+  if (n_send + n_recv > 0) {
+#define B2N_NCCL(expr)                                                                             \
+  do {                                                                                             \
+    ncclResult_t r__ = (expr);                                                                     \
+    B2N_REQUIRE(r__ == ncclSuccess, B2N_ERR_COMM, "%s: %s", #expr, ncclGetErrorString(r__));       \
+  } while (0)
+    B2N_NCCL(ncclGroupStart());
+    for (size_t i = 0; i < n_send; i++) {
+      const size_t a = (size_t)mp.send_idx[i];
+      const int t = mp.send_rank[i];
+      B2N_NCCL(ncclSend(src.log_odds + a * c.gstride, (size_t)c.gstride, ncclDouble, t, h->comm, h->stream));
+      B2N_NCCL(ncclSend(src.d2 + a * c.gstride, (size_t)c.gstride, ncclUint32, t, h->comm, h->stream));
+      B2N_NCCL(ncclSend(src.nxt + a * c.nxt_stride, (size_t)c.nxt_stride * 2, ncclUint8, t, h->comm, h->stream));
+      B2N_NCCL(ncclSend(src.bkt + a * c.bkt_stride, (size_t)c.bkt_stride * 2, ncclUint8, t, h->comm, h->stream));
+      B2N_NCCL(ncclSend(src.meta + a, sizeof(PfParticle), ncclUint8, t, h->comm, h->stream));
+    }
+    for (size_t i = 0; i < n_recv; i++) {
+      const size_t m = (size_t)mp.recv_slot[i];
+      const int s = mp.recv_rank[i];
+      B2N_NCCL(ncclRecv(dst.log_odds + m * c.gstride, (size_t)c.gstride, ncclDouble, s, h->comm, h->stream));
+      B2N_NCCL(ncclRecv(dst.d2 + m * c.gstride, (size_t)c.gstride, ncclUint32, s, h->comm, h->stream));
+      B2N_NCCL(ncclRecv(dst.nxt + m * c.nxt_stride, (size_t)c.nxt_stride * 2, ncclUint8, s, h->comm, h->stream));
+      B2N_NCCL(ncclRecv(dst.bkt + m * c.bkt_stride, (size_t)c.bkt_stride * 2, ncclUint8, s, h->comm, h->stream));
+      B2N_NCCL(ncclRecv(dst.meta + m, sizeof(PfParticle), ncclUint8, s, h->comm, h->stream));
+    }
+    B2N_NCCL(ncclGroupEnd());
+#undef B2N_NCCL
+  }
+  // fan-out of received particles inside the new set (slots are distinct from their sources)
+  rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, dst, dst, h->d_idx + h->N);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  return B2N_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -429,7 +530,7 @@ void b2n_pf_destroy(b2n_pf *h)
   free_planes(h->set[0]); free_planes(h->set[1]);
   cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_w); cudaFree(h->d_anc);
   cudaFree(h->d_ext); cudaFree(h->d_samples); cudaFree(h->d_spill); cudaFree(h->d_stats); cudaFree(h->d_best); cudaFree(h->d_map);
-  cudaFree(h->d_lik);
+  cudaFree(h->d_lik); cudaFree(h->d_idx);
   if (h->h_scan) cudaFreeHost(h->h_scan);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->h_best) cudaFreeHost(h->h_best);
@@ -552,18 +653,15 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   if (h->last_resampled) {
     B2N_CUDA(cudaMemcpyAsync(h->h_anc.data(), h->d_anc, sizeof(int32_t) * h->n_total, cudaMemcpyDeviceToHost, h->stream));
     B2N_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->nranks > 1) {
-      for (int m = 0; m < h->N; m++) {
-        const int a = h->h_anc[h->offset + m];
-        B2N_REQUIRE(a >= h->offset && a < h->offset + h->N, B2N_ERR_UNSUPPORTED,
-                    "resampling picked particle %d of another rank for slot %d: cross-GPU particle migration is not built yet", a, h->offset + m);
-      }
-    }
     PfPlanes &dst = h->set[h->cur ^ 1];
     dim3 grid(8, h->N);
-    rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, pl, dst, h->d_anc, h->nranks > 1 ? h->offset : 0);
-    B2N_CUDA(cudaGetLastError());
-    h->launches++;
+    if (h->nranks > 1) {
+      if (int rc = migrate_particles(h, pl, dst)) return rc;
+    } else {
+      rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, pl, dst, h->d_anc);
+      B2N_CUDA(cudaGetLastError());
+      h->launches++;
+    }
     h->cur ^= 1;
   } else {
     for (int i = 0; i < h->n_total; i++) h->h_anc[i] = i;
@@ -732,7 +830,7 @@ int b2n_pf_normalize_resample(b2n_pf *h)
   h->last_resampled = h->h_status[2];
   if (h->last_resampled) {
     dim3 grid(8, h->N);
-    rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, pl, h->set[h->cur ^ 1], h->d_anc, 0);
+    rbpf_copy_particles_kernel<<<grid, 256, 0, h->stream>>>(c, pl, h->set[h->cur ^ 1], h->d_anc);
     B2N_CUDA(cudaGetLastError());
     h->launches++;
     h->cur ^= 1;
@@ -847,6 +945,38 @@ int b2n_pf_host_tables(const b2n_pf_params *params, double constants[4], double 
   if (beam_cs) std::copy(beam.begin(), beam.end(), beam_cs);
   *pz_n = c.pz_n;
   if (pz) std::copy(table.begin(), table.begin() + std::min(pz_cap, table.size()), pz);
+  return B2N_OK;
+}
+
+int b2n_pf_plan_migration(const int32_t *ancestors, int n_total, int rank, int nranks, int32_t *copy1, int32_t *copy2, int32_t *recv,
+                          size_t recv_cap, int *n_recv, int32_t *send, size_t send_cap, int *n_send)
+{
+  B2N_REQUIRE(ancestors && copy1 && copy2 && n_recv && n_send, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && n_total > 0 && n_total % nranks == 0, B2N_ERR_INVALID_ARGUMENT,
+              "sharding must be even: n_total = %d over %d ranks", n_total, nranks);
+  for (int i = 0; i < n_total; i++)
+    B2N_REQUIRE(ancestors[i] >= 0 && ancestors[i] < n_total, B2N_ERR_INVALID_ARGUMENT, "ancestor %d of slot %d out of range", ancestors[i], i);
+  const int n_local = n_total / nranks;
+  MigrationPlan mp;
+  plan_migration(ancestors, n_total, n_local, rank, nranks, mp);
+  std::copy(mp.copy1.begin(), mp.copy1.end(), copy1);
+  std::copy(mp.copy2.begin(), mp.copy2.end(), copy2);
+  *n_recv = (int)mp.recv_slot.size();
+  *n_send = (int)mp.send_idx.size();
+  for (size_t i = 0; i < mp.recv_slot.size() && recv && 3 * i + 2 < recv_cap; i++) {
+    recv[3 * i] = mp.recv_slot[i]; recv[3 * i + 1] = mp.recv_anc[i]; recv[3 * i + 2] = mp.recv_rank[i];
+  }
+  for (size_t i = 0; i < mp.send_idx.size() && send && 2 * i + 1 < send_cap; i++) {
+    send[2 * i] = mp.send_idx[i]; send[2 * i + 1] = mp.send_rank[i];
+  }
+  return B2N_OK;
+}
+
+int b2n_pf_get_migration(const b2n_pf *h, int *received, int *sent)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (received) *received = h->last_migrated_in;
+  if (sent) *sent = h->last_migrated_out;
   return B2N_OK;
 }
 

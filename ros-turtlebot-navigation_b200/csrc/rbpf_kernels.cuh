@@ -1115,12 +1115,14 @@ __global__ void rbpf_scatter_weights_kernel(PfParticle *meta, const double *w, i
   if (i < n) meta[i].weight = w[i];
 }
 
-// particle m of dst <- particle ancestors[m] of src, plane by plane with 16-byte accesses; blockIdx.y = m
+// particle m of dst <- particle src_index[m] of src (skipped when negative), plane by plane with 16-byte accesses;
+// blockIdx.y = m.  src_index holds LOCAL particle indices (the host turns global ancestors into them).
 __global__ void __launch_bounds__(256) rbpf_copy_particles_kernel(const __grid_constant__ PfConst c, const PfPlanes src, const PfPlanes dst,
-                                                                   const int32_t *ancestors, int anc_offset)
+                                                                   const int32_t *src_index)
 {
   const int m = blockIdx.y;
-  const int a = ancestors[anc_offset + m] - anc_offset;      // local source index (host guarantees it is local)
+  const int a = src_index[m];
+  if (a < 0) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const uint4 *s0 = reinterpret_cast<const uint4 *>(src.log_odds + (size_t)a * c.gstride);
   uint4 *d0 = reinterpret_cast<uint4 *>(dst.log_odds + (size_t)m * c.gstride);
