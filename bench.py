@@ -47,7 +47,7 @@ def workload_config(n_gpus):
         "rollouts_per_gpu": K_ROLLOUTS, "rollouts_total": K_ROLLOUTS * n_gpus, "horizon_steps": 64,
         "noise": "Philox4x32-10 counter-based + binary32 Box-Muller, seed 42",
         "l2": "state tensor written round-robin into %d buffers (%.0f MB) > 126 MB L2" % (STATE_RING, STATE_RING * K_ROLLOUTS * 64 * 12 / 1e6),
-        "sharding": "rollouts" if n_gpus > 1 else "none",
+        "sharding": "rollouts; [T][6] partial exchanged inside the update kernel over NVLink peer memory (--exchange nccl: ncclAllGather)" if n_gpus > 1 else "none",
     }
 
 
@@ -169,20 +169,32 @@ def rbpf_cpu(kind, budget_s=12.0, n_particles=64):
                       % (done, n_particles, RBPF_N, el)}
 
 
-def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
-    """BASELINE configs[2]: RBPF 4096 particles, 360-beam synthetic lidar, 200x200 map, motion-model branch:
-    sample + beam weighting + ray integration + distance field + normalise + resample, every scan."""
+def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=None):
+    """BASELINE configs[2]: RBPF 4096 particles (per GPU: weak scaling), 360-beam synthetic lidar, 200x200 map,
+    motion-model branch: sample + beam weighting + ray integration + distance field + normalise + resample, every
+    scan.  At N > 1 GPUs the weights travel with one allgather per scan, every rank runs the identical walk and
+    particles whose ancestor lives on another GPU migrate (ncclSend/ncclRecv)."""
     poses, twists, scans = rbpf_inputs(n_scans + warmup)
-    f = pkg.bmapping.make_filter(__import__("_oracle").pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]),
-                                                                 motion_noise=RBPF_MOTION_NOISE))
+    q = __import__("_oracle").pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]), motion_noise=RBPF_MOTION_NOISE)
+    if world > 1:
+        f = pkg.bmapping.make_filter(q, particle_offset=rank * RBPF_N, particles_total=world * RBPF_N, device=local)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    else:
+        f = pkg.bmapping.make_filter(q, device=local)
     f.seed(1)
     f.setKernelTiming(True)
     ms = [0.0, 0.0, 0.0]
-    resampled, wall = 0, 0.0
+    resampled, wall, migrated = 0, 0.0, 0
     n0 = f.launchCount()
     for i in range(n_scans + warmup):
         if i == warmup:
             n0 = f.launchCount()
+            if world > 1:
+                dist.barrier()
         t0 = time.perf_counter()
         f.SLAM(scans[i], pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
         dt_wall = time.perf_counter() - t0
@@ -192,9 +204,18 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
             for j in range(3):
                 ms[j] += k[j]
             resampled += f.resampleInfo()[1]
+            migrated += f.migration()[0]
     launches = f.launchCount() - n0
+    if world > 1:
+        t = torch.tensor(ms + [wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = [float(v) for v in t[:3]], float(t[3])
+        mg = torch.tensor([migrated], dtype=torch.int64, device="cuda")
+        dist.all_reduce(mg)
+        migrated = int(mg.item())
     dev_ms = sum(ms)
     df_ms = ms[1] / n_scans
+    n_all = RBPF_N * world
     achieved = RBPF_N * RBPF_DF_BYTES_PER_PARTICLE / (df_ms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
@@ -203,16 +224,17 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("rbpf_distance_field_kernel_dram_bytes_per_launch")
     out = {
-        "metric": "rbpf_particle_updates_per_sec", "unit": "particle-updates/s",
-        "value": RBPF_N * n_scans / (dev_ms * 1e-3),
-        "config": {"workload": "RBPF 4096 particles, 360-beam synthetic lidar, 200x200 occupancy grid (BASELINE configs[2]), motion-model branch",
-                   "particles": RBPF_N, "beams": RBPF_BEAMS, "cells": RBPF_CELLS, "scans": n_scans, "warmup_scans": warmup,
-                   "resampled_scans": int(resampled),
-                   "l2": "per-particle planes total %.1f GB >> 126 MB L2" % (RBPF_N * RBPF_CELLS * 12 / 1e9)},
+        "metric": "rbpf_particle_updates_per_sec", "unit": "particle-updates/s", "n_gpus": world, "scaling": "weak",
+        "value": n_all * n_scans / (dev_ms * 1e-3),
+        "config": {"workload": "RBPF 4096 particles per GPU, 360-beam synthetic lidar, 200x200 occupancy grid (BASELINE configs[2]), motion-model branch",
+                   "particles_per_gpu": RBPF_N, "particles_total": n_all, "beams": RBPF_BEAMS, "cells": RBPF_CELLS, "scans": n_scans,
+                   "warmup_scans": warmup, "resampled_scans": int(resampled), "particles_migrated_between_gpus": int(migrated),
+                   "sharding": "particles; weights allgather + identical walk + ncclSend/ncclRecv migration" if world > 1 else "none",
+                   "l2": "per-particle planes total %.1f GB per GPU >> 126 MB L2" % (RBPF_N * RBPF_CELLS * 12 / 1e9)},
         "ms_per_scan": dev_ms / n_scans,
         "kernel_ms_per_scan": {"update(sample+weight+rays)": ms[0] / n_scans, "distance_field": df_ms,
                                "normalise+resample+copy": ms[2] / n_scans},
-        "e2e": {"value": RBPF_N * n_scans / wall, "unit": "particle-updates/s", "ms_per_scan": 1e3 * wall / n_scans,
+        "e2e": {"value": n_all * n_scans / wall, "unit": "particle-updates/s", "ms_per_scan": 1e3 * wall / n_scans,
                 "h2d_bytes_per_step": 4 * RBPF_BEAMS + 72, "d2h_bytes_per_step": 16,
                 "note": "synchronous SLAM(): host scan + twist + odometry in, status / N_eff / resample flag out"},
         "gpu_launches": int(launches),
@@ -308,6 +330,12 @@ def run_ours(args):
             uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         mppi.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        if args.exchange == "p2p":
+            # exchange inside the update kernel over NVLink peer memory: gather every rank's CUDA IPC handle
+            mine = torch.frombuffer(bytearray(mppi.p2pExport(world)), dtype=torch.uint8).cuda()
+            hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(hs, mine)
+            mppi.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
     stream = torch.cuda.current_stream()
     mppi.setStream(stream.cuda_stream)
     mppi.setStateRing(STATE_RING)
@@ -399,9 +427,14 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_oracle_port()
-        if world == 1 and not args.no_rbpf:
-            line["rbpf"] = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3)
-            if not args.no_cpu:
+    rbpf = None
+    if not args.no_rbpf:
+        mppi.close()
+        rbpf = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3, rank, world, local, dist if world > 1 else None)
+    if rank == 0:
+        if rbpf is not None:
+            line["rbpf"] = rbpf
+            if world == 1 and not args.no_cpu:
                 line["rbpf"]["cpu_baseline"] = rbpf_cpu("port")
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -418,6 +451,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-rbpf", action="store_true", help="skip the RBPF leg (BASELINE configs[2])")
     ap.add_argument("--rbpf-scans", type=int, default=20)
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the [T][6] softmax partial travels - inside the update kernel over NVLink peer memory, or ncclAllGather")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 2000:

@@ -126,6 +126,14 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
  * by the caller (e.g. a torch.distributed broadcast). */
 int b2n_comm_unique_id(void *out128);
 int b2n_mppi_comm_init(b2n_mppi *h, int rank, int nranks, const void *unique_id128);
+/* Same sharding, exchange over NVLink peer memory instead of NCCL (ranks = processes on ONE node, peer access between
+ * their GPUs): merge of the CTA partials, push of the [T][6] result into every rank's exchange area, wait for the
+ * others and the control update are ONE kernel (mppi_exchange_update_kernel).  Every rank calls
+ * b2n_mppi_p2p_export (allocates its area, returns a 64-byte cudaIpcMemHandle_t), the caller gathers the handles of
+ * all ranks in rank order (nranks x 64 bytes) and passes them to b2n_mppi_p2p_init.  Takes precedence over the NCCL
+ * path once initialised. */
+int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64);
+int b2n_mppi_p2p_init(b2n_mppi *h, int rank, int nranks, const void *handles);
 
 /* ======================================================================================== RBPF */
 

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "b2n_mppi_time_rollout": (C.c_int, [_vp, D, D, D, C.c_int, _P(D)]),
     "b2n_comm_unique_id": (C.c_int, [_vp]),
     "b2n_mppi_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b2n_mppi_p2p_export": (C.c_int, [_vp, C.c_int, _vp]),
+    "b2n_mppi_p2p_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2n_pf_create": (C.c_int, [_P(PfParams), _P(_vp)]),
     "b2n_pf_destroy": (None, [_vp]),
     "b2n_pf_slam": (C.c_int, [_vp, _vp, C.c_int, _P(D), _P(D), _P(D), C.c_int, _P(D)]),

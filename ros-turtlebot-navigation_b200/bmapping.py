@@ -198,6 +198,12 @@ class ParticleFilter:
     def setHeapCapacity(self, entries):
         _capi.check(self._lib.b2n_pf_set_heap_capacity(self._h, int(entries)))
 
+    def migration(self):
+        """(particles received from, sent to) other ranks by the last SLAM()"""
+        a, b = C.c_int(), C.c_int()
+        _capi.check(self._lib.b2n_pf_get_migration(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def commInit(self, rank, nranks, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _capi.check(self._lib.b2n_pf_comm_init(self._h, rank, nranks, buf))

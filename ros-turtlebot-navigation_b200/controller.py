@@ -146,6 +146,17 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_time_rollout(self._h, ps.x, ps.y, ps.theta, int(launches), C.byref(ms)))
         return ms.value
 
+    def p2pExport(self, nranks):
+        """allocate this rank's exchange area; returns the 64-byte CUDA IPC handle to hand to the other ranks"""
+        buf = C.create_string_buffer(64)
+        _capi.check(self._lib.b2n_mppi_p2p_export(self._h, int(nranks), buf))
+        return buf.raw
+
+    def p2pInit(self, rank, nranks, handles):
+        """handles: the nranks x 64 bytes of every rank's p2pExport(), in rank order"""
+        buf = C.create_string_buffer(bytes(handles), 64 * int(nranks))
+        _capi.check(self._lib.b2n_mppi_p2p_init(self._h, int(rank), int(nranks), buf))
+
     def commInit(self, rank, nranks, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _capi.check(self._lib.b2n_mppi_comm_init(self._h, rank, nranks, buf))

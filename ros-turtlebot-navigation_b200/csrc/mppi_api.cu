@@ -56,6 +56,13 @@ struct b2n_mppi
   // sharding
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory exchange (CUDA IPC): this rank's area and the mapped areas of all ranks
+  void *xchg = nullptr;                  // [2][nranks][T] x (6 doubles) followed by [2][nranks][T] flags
+  size_t xchg_bytes = 0, xchg_flag_offset = 0;
+  int xchg_nranks = 0;
+  std::vector<void *> peer_base;         // mapped peer areas (own entry = xchg)
+  bool p2p_ready = false;
+  unsigned long long xchg_call = 0;
 
   // accounting
   uint64_t launches = 0;
@@ -225,6 +232,25 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   u.out = h->d_out_host;               // mapped pinned memory: the controls land on the host without a copy operation
   u.stepstats = h->d_stepstats;
   u.merged = h->d_merged;
+  if (h->nranks > 1 && h->p2p_ready) {
+    // merge + exchange over NVLink peer memory + update in one kernel (mppi_exchange_update_kernel)
+    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
+    MppiXchgArgs xa;
+    std::memset(&xa, 0, sizeof(xa));
+    for (int r = 0; r < h->nranks; r++) {
+      xa.peer_data[r] = static_cast<double *>(h->peer_base[r]);
+      xa.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->peer_base[r]) + h->xchg_flag_offset);
+    }
+    xa.rank = h->rank; xa.nranks = h->nranks; xa.call_id = ++h->xchg_call;
+    mppi_exchange_update_kernel<<<h->T, kMppiUpdateThreads, 0, h->stream>>>(u, xa);
+    B2N_CUDA(cudaGetLastError());
+    h->launches++;
+    h->cur ^= 1;
+    h->call++;
+    h->ext_armed = false;
+    h->pending = true;
+    return B2N_OK;
+  }
   if (h->nranks > 1) {
     // local merge -> one allgather of [T][6] doubles -> identical update on every rank
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 1;
@@ -327,6 +353,9 @@ void b2n_mppi_destroy(b2n_mppi *h)
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) ncclCommDestroy(h->comm);
+  for (int r = 0; r < (int)h->peer_base.size(); r++)
+    if (h->peer_base[r] && h->peer_base[r] != h->xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
+  cudaFree(h->xchg);
   for (auto e : h->ev) cudaEventDestroy(e);
   cudaFree(h->d_u[0]); cudaFree(h->d_u[1]); cudaFree(h->d_states); cudaFree(h->d_partials);
   cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_stepstats);
@@ -596,6 +625,47 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   h->launches += (uint64_t)launches;
   *avg_ms = (double)ms / launches;
+  return B2N_OK;
+}
+
+int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64)
+{
+  B2N_REQUIRE(h && handle64, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(nranks >= 2 && nranks <= kMppiMaxRanks, B2N_ERR_INVALID_ARGUMENT, "nranks must be in [2, %d]", kMppiMaxRanks);
+  B2N_REQUIRE(!h->xchg, B2N_ERR_INVALID_ARGUMENT, "exchange area already exported");
+  if (int rc = set_device(h)) return rc;
+  const size_t slots = (size_t)2 * nranks * h->T;
+  h->xchg_flag_offset = slots * 6 * sizeof(double);
+  h->xchg_bytes = h->xchg_flag_offset + slots * sizeof(unsigned long long);
+  B2N_CUDA(cudaMalloc(&h->xchg, h->xchg_bytes));
+  B2N_CUDA(cudaMemset(h->xchg, 0, h->xchg_bytes));
+  h->xchg_nranks = nranks;
+  cudaIpcMemHandle_t ipc;
+  static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  B2N_CUDA(cudaIpcGetMemHandle(&ipc, h->xchg));
+  std::memcpy(handle64, &ipc, sizeof(ipc));
+  return B2N_OK;
+}
+
+int b2n_mppi_p2p_init(b2n_mppi *h, int rank, int nranks, const void *handles)
+{
+  B2N_REQUIRE(h && handles, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->xchg && nranks == h->xchg_nranks && rank >= 0 && rank < nranks, B2N_ERR_INVALID_ARGUMENT,
+              "b2n_mppi_p2p_export(h, %d, ...) must come first on every rank", nranks);
+  if (int rc = set_device(h)) return rc;
+  h->peer_base.assign(nranks, nullptr);
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) { h->peer_base[r] = h->xchg; continue; }
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, static_cast<const char *>(handles) + (size_t)r * sizeof(ipc), sizeof(ipc));
+    cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[r], ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaIpcOpenMemHandle for rank %d: %s (peer access between the GPUs is required)", r, cudaGetErrorString(e));
+      return B2N_ERR_COMM;
+    }
+  }
+  h->rank = rank; h->nranks = nranks; h->p2p_ready = true; h->xchg_call = 0;
   return B2N_OK;
 }
 

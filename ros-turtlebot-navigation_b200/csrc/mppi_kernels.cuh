@@ -388,20 +388,16 @@ __global__ void __launch_bounds__(kMppiThreads, (S >= 8 ? 1 : (S >= 4 ? 3 : 4)))
 // mppi.cpp:112-137 for that step, written one slot to the left (the receding-horizon shift).
 constexpr int kMppiUpdateThreads = 128;
 
-__global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const MppiUpdateArgs a)
+// merge of the step's partials by one CTA: minimum first, then every partial rescaled once (independent
+// exponentials), plain sums.  The result is valid in thread 0.
+__device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int T, int t, double inv_lambda, double &m,
+                                                 double &S, double &A, double &B, double &DL, double &DR)
 {
   __shared__ double red[kMppiUpdateThreads / 32][6];
-  const int t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = a.T;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
-
-  // launched with programmatic stream serialization: wait here until the producing grid has finished and its
-  // partials are visible (a no-op for an ordinary launch)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // phase 1: the step's minimum over all partials
-  double m = inf;
-  for (int p = threadIdx.x; p < a.n_partials; p += kMppiUpdateThreads) m = fmin(m, a.partials[((size_t)p * T + t) * 6]);
+  m = inf;
+  for (int p = threadIdx.x; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, partials[((size_t)p * T + t) * 6]);
   m = warp_min(m);
   if (lane == 0) red[warp][0] = m;
   __syncthreads();
@@ -409,13 +405,12 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
 #pragma unroll
   for (int w = 1; w < kMppiUpdateThreads / 32; w++) m = fmin(m, red[w][0]);
   __syncthreads();
-  // phase 2: every partial rescaled once to that minimum (independent exponentials), plain sums
-  double S = 0.0, A = 0.0, B = 0.0, DL = 0.0, DR = 0.0;
-  for (int p = threadIdx.x; p < a.n_partials; p += kMppiUpdateThreads) {
-    const double2 *c = reinterpret_cast<const double2 *>(a.partials + ((size_t)p * T + t) * 6);
+  S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
+  for (int p = threadIdx.x; p < n_partials; p += kMppiUpdateThreads) {
+    const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
     const double2 c0 = c[0], c1 = c[1], c2 = c[2];
     if (c0.x != inf) {
-      const double f = (c0.x == m) ? 1.0 : mppi_exp_neg((m - c0.x) * a.inv_lambda);
+      const double f = (c0.x == m) ? 1.0 : mppi_exp_neg((m - c0.x) * inv_lambda);
       S = fma(c0.y, f, S); A = fma(c1.x, f, A); B = fma(c1.y, f, B);
     }
     DL += c2.x; DR += c2.y;
@@ -423,16 +418,17 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
   if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  for (int w = 1; w < kMppiUpdateThreads / 32; w++) {
-    S += red[w][1]; A += red[w][2]; B += red[w][3]; DL += red[w][4]; DR += red[w][5];
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kMppiUpdateThreads / 32; w++) {
+      S += red[w][1]; A += red[w][2]; B += red[w][3]; DL += red[w][4]; DR += red[w][5];
+    }
   }
+}
 
-  if (a.merge_only) {
-    double *o = a.merged + (size_t)t * 6;
-    o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
-    return;
-  }
+// the control update of mppi.cpp:112-137 for step t from the fully merged sums (one thread)
+__device__ __forceinline__ void mppi_apply_update(const MppiUpdateArgs &a, int t, double m, double S, double A, double B, double DL, double DR)
+{
+  const int T = a.T;
   // w_k = exp(-(J_k - min)/lambda) + 1e-8, normalised (mppi.cpp:117-118)
   const double sumw = S + a.k_total * 1e-8;
   const double inv = 1.0 / sumw;
@@ -445,6 +441,90 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   if (t == T - 1) { a.u_next[T - 1] = a.uinit[0]; a.u_next[2 * T - 1] = a.uinit[1]; }   // mppi.cpp:136-137
   a.stepstats[2 * t] = m;
   a.stepstats[2 * t + 1] = sumw;
+}
+
+__global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const MppiUpdateArgs a)
+{
+  const int t = blockIdx.x;
+  // launched with programmatic stream serialization: wait here until the producing grid has finished and its
+  // partials are visible (a no-op for an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  double m, S, A, B, DL, DR;
+  mppi_block_merge(a.partials, a.n_partials, a.T, t, a.inv_lambda, m, S, A, B, DL, DR);
+  if (threadIdx.x != 0) return;
+  if (a.merge_only) {
+    double *o = a.merged + (size_t)t * 6;
+    o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
+    return;
+  }
+  mppi_apply_update(a, t, m, S, A, B, DL, DR);
+}
+
+// ---- sharded rollouts: merge + exchange + update in ONE kernel over NVLink peer memory ----------------
+// Every rank owns an exchange area [2 call parities][nranks][T] x {6 doubles, flag}; peer[j] is rank j's area mapped
+// into this process (CUDA IPC).  CTA t merges this rank's CTA partials for step t, thread j stores the 48-byte result
+// straight into rank j's area (slot = this rank), fences at system scope and publishes the call id in the slot's
+// flag; it then spins on the flag of slot j in its OWN area and reads rank j's result.  Thread 0 folds the nranks
+// results in rank order (identical on every rank, so the plan stays replicated without a broadcast) and applies the
+// update.  No NCCL call, no extra launch: the exchange costs one NVLink round trip inside the update kernel.  A slot
+// of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's data of
+// call c + 1, which was sent after this rank finished reading call c: two parities are enough.
+constexpr int kMppiMaxRanks = 64;
+
+struct MppiXchgArgs
+{
+  double *peer_data[kMppiMaxRanks];               // rank j's data area  [2][nranks][T][6]
+  unsigned long long *peer_flag[kMppiMaxRanks];   // rank j's flag area  [2][nranks][T]
+  int rank, nranks;
+  unsigned long long call_id;                     // 1-based, strictly increasing
+};
+
+__global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kernel(const MppiUpdateArgs a, const __grid_constant__ MppiXchgArgs x)
+{
+  __shared__ double mine[6];
+  __shared__ double all[kMppiMaxRanks][6];
+  const int t = blockIdx.x, T = a.T, j = threadIdx.x;
+  const int par = (int)(x.call_id & 1ull);
+  double m, S, A, B, DL, DR;
+  mppi_block_merge(a.partials, a.n_partials, T, t, a.inv_lambda, m, S, A, B, DL, DR);
+  if (j == 0) { mine[0] = m; mine[1] = S; mine[2] = A; mine[3] = B; mine[4] = DL; mine[5] = DR; }
+  __syncthreads();
+  for (int r = j; r < x.nranks; r += kMppiUpdateThreads) {
+    // push to rank r (including this rank's own area: one code path)
+    const size_t slot = ((size_t)par * x.nranks + x.rank) * T + t;
+    double2 *dst = reinterpret_cast<double2 *>(x.peer_data[r] + slot * 6);
+    dst[0] = make_double2(mine[0], mine[1]);
+    dst[1] = make_double2(mine[2], mine[3]);
+    dst[2] = make_double2(mine[4], mine[5]);
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(x.peer_flag[r] + slot), "l"(x.call_id) : "memory");
+  }
+  for (int r = j; r < x.nranks; r += kMppiUpdateThreads) {
+    // pull rank r's result out of this rank's own area
+    const size_t slot = ((size_t)par * x.nranks + r) * T + t;
+    const unsigned long long *flag = x.peer_flag[x.rank] + slot;
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    } while (seen != x.call_id);
+    const double *src = x.peer_data[x.rank] + slot * 6;
+#pragma unroll
+    for (int i = 0; i < 6; i++) all[r][i] = __ldcv(src + i);
+  }
+  __syncthreads();
+  if (j != 0) return;
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  m = inf;
+  for (int r = 0; r < x.nranks; r++) m = fmin(m, all[r][0]);
+  S = A = B = DL = DR = 0.0;
+  for (int r = 0; r < x.nranks; r++) {
+    if (all[r][0] != inf) {
+      const double f = (all[r][0] == m) ? 1.0 : mppi_exp_neg((m - all[r][0]) * a.inv_lambda);
+      S = fma(all[r][1], f, S); A = fma(all[r][2], f, A); B = fma(all[r][3], f, B);
+    }
+    DL += all[r][4]; DR += all[r][5];
+  }
+  mppi_apply_update(a, t, m, S, A, B, DL, DR);
 }
 
 // parity tap: the normalised weights the reference materialises at mppi.cpp:117-118
