@@ -1,6 +1,7 @@
 // mppi_api.cu - extern "C" MPPI entry points of libb2nav (see include/b2nav.h).
 // Host side of controller::MPPI (reference: controller/src/controller/mppi.cpp:28-69,72-140).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,7 @@ struct b2n_mppi
   double *d_stepstats = nullptr;         // [T][2]
   double *h_out = nullptr;               // pinned, mapped [2]: the update kernel writes the controls here
   double *d_out_host = nullptr;          // device view of h_out
+  unsigned long long out_seq = 0;        // sequence number of the last enqueued call (completion word in h_out[2])
   bool use_pdl = false;                  // programmatic dependent launch of the update kernel: measured 2.4 us per call SLOWER at
                                          // K = 16384 (the early-scheduled update CTAs take residency from the rollout grid); B2N_MPPI_PDL=1 turns it on
   double *d_ext = nullptr;               // [K][T][2]
@@ -230,6 +232,8 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   u.u_cur = h->d_u[h->cur];
   u.u_next = h->d_u[h->cur ^ 1];
   u.out = h->d_out_host;               // mapped pinned memory: the controls land on the host without a copy operation
+  u.out_seq = reinterpret_cast<unsigned long long *>(h->d_out_host + 2);
+  u.seq = ++h->out_seq;
   u.stepstats = h->d_stepstats;
   u.merged = h->d_merged;
   if (h->nranks > 1 && h->p2p_ready) {
@@ -338,7 +342,8 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_TRY(cudaMalloc(&h->d_merged, (size_t)T * 6 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_out, 2 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_stepstats, (size_t)T * 2 * sizeof(double)));
-  B2N_TRY(cudaHostAlloc(&h->h_out, 2 * sizeof(double), cudaHostAllocMapped));
+  B2N_TRY(cudaHostAlloc(&h->h_out, 4 * sizeof(double), cudaHostAllocMapped));
+  std::memset(h->h_out, 0, 4 * sizeof(double));
   B2N_TRY(cudaHostGetDevicePointer(&h->d_out_host, h->h_out, 0));
   if (const char *env = std::getenv("B2N_MPPI_PDL")) h->use_pdl = env[0] == '1';
   B2N_TRY(cudaStreamSynchronize(h->stream));
@@ -399,7 +404,18 @@ int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur)
 {
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
   B2N_REQUIRE(h->pending, B2N_ERR_INVALID_ARGUMENT, "b2n_mppi_wait: nothing enqueued");
-  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  // the update kernel publishes the controls and then the call's sequence number in mapped pinned memory: poll that
+  // word (about a microsecond after the store) instead of a stream synchronisation; every so often make sure the
+  // stream has not failed
+  volatile unsigned long long *seq = reinterpret_cast<volatile unsigned long long *>(h->h_out + 2);
+  for (unsigned spins = 0; *seq != h->out_seq; spins++) {
+    if ((spins & 0xFFFFu) == 0xFFFFu) {
+      const cudaError_t e = cudaStreamQuery(h->stream);
+      if (e == cudaSuccess) break;                  // finished: the word is visible by now
+      if (e != cudaErrorNotReady) { set_error("stream failed while waiting for the controls: %s", cudaGetErrorString(e)); return B2N_ERR_CUDA; }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   if (ul) *ul = h->h_out[0];
   if (ur) *ur = h->h_out[1];
   return B2N_OK;

@@ -66,7 +66,9 @@ struct MppiUpdateArgs
   double uinit[2];
   const double *u_cur;     // [2][T]
   double *u_next;          // [2][T]
-  double *out;             // [2] first control of the updated plan
+  double *out;             // [2] first control of the updated plan (mapped pinned host memory)
+  unsigned long long *out_seq;   // completion word next to it: set to `seq` after the controls are visible to the host
+  unsigned long long seq;
   double *stepstats;       // [T][2] (min J, sum w) for the weights tap
   double *merged;          // [T][6] when merge_only
 };
@@ -436,7 +438,14 @@ __device__ __forceinline__ void mppi_apply_update(const MppiUpdateArgs &a, int t
   double nr = a.u_cur[T + t] + (B + 1e-8 * DR) * inv;
   nl = fmin(fmax(nl, -a.umax), a.umax);                     // mppi.cpp:124-125
   nr = fmin(fmax(nr, -a.umax), a.umax);
-  if (t == 0) { a.out[0] = nl; a.out[1] = nr; }             // mppi.cpp:129-131
+  if (t == 0) {                                             // mppi.cpp:129-131
+    a.out[0] = nl; a.out[1] = nr;
+    if (a.out_seq) {
+      // the host polls this word instead of paying a stream synchronisation for 16 bytes
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.out_seq), "l"(a.seq) : "memory");
+    }
+  }
   else { a.u_next[t - 1] = nl; a.u_next[T + t - 1] = nr; }  // mppi.cpp:134
   if (t == T - 1) { a.u_next[T - 1] = a.uinit[0]; a.u_next[2 * T - 1] = a.uinit[1]; }   // mppi.cpp:136-137
   a.stepstats[2 * t] = m;
