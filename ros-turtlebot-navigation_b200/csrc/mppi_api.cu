@@ -162,6 +162,7 @@ MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
   a.sigL = std::sqrt(p.ul_var);       // mppi.cpp:176-177
   a.sigR = std::sqrt(p.ur_var);
   a.x0[0] = x; a.x0[1] = y; a.x0[2] = theta;   // mppi.cpp:75-76
+  a.cos0 = std::cos(theta); a.sin0 = std::sin(theta);
   a.T = h->T; a.K = h->K; a.k_offset = p.rollout_offset;
   a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.call = h->call;
   a.external_noise = h->ext_armed ? 1 : 0;

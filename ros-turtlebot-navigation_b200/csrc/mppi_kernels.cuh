@@ -42,6 +42,7 @@ struct MppiArgs
   double Q[3], R[2], P1[3];
   double inv_lambda, sigL, sigR;
   double x0[3], xd[3];
+  double cos0, sin0;          // of the start heading x0[2], from the host's libm
   int T, K, k_offset;
   uint32_t seed_lo, seed_hi, call;
   int external_noise, capture, tma_store;
@@ -142,8 +143,7 @@ __global__ void __launch_bounds__(kMppiThreads, (S >= 8 ? 1 : (S >= 4 ? 3 : 4)))
   const bool tma_store = FAST || a.tma_store;
   float *stage = stage_base + warp * 2 * (R * TP * 3);
 
-  double sin0, cos0;
-  sincos(a.x0[2], &sin0, &cos0);
+  const double sin0 = a.sin0, cos0 = a.cos0;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
 
   // online-softmax accumulators of this lane's steps: (min J, sum e, sum e*duL, sum e*duR, sum duL, sum duR) x S
