@@ -105,6 +105,11 @@ int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count);
 int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int ysize, double xmin, double ymin,
                                 double resolution, double weight, double d0, double off_map);
 
+/* The same term fed on the device: allocates the field inside the handle and returns its DEVICE
+ * address, for a producer that fills it without a host round trip (b2n_pf_write_distance_field below). */
+int b2n_mppi_obstacle_field_device(b2n_mppi *h, int xsize, int ysize, double xmin, double ymin, double resolution, double weight,
+                                   double d0, double off_map, float **device_field);
+
 /* Launch on a caller-owned cudaStream_t (pass the pointer value); NULL restores the handle's own */
 int b2n_mppi_set_stream(b2n_mppi *h, void *cuda_stream);
 /* Write the K*T*3 state tensor round-robin into n buffers (n*K*T*12 bytes) so that back-to-back
@@ -205,6 +210,13 @@ int b2n_pf_likelihoods(b2n_pf *h, const float *scan, int n_beams, double *out, s
 /* normalizeWeights + effectiveParticles + lowVarianceResampling alone (particle_filter.cpp:244-249) */
 int b2n_pf_normalize_resample(b2n_pf *h);
 int b2n_pf_set_stream(b2n_pf *h, void *cuda_stream);
+/* map geometry of the handle: origin and resolution (cells: b2n_pf_grid_size) */
+int b2n_pf_geometry(const b2n_pf *h, double *xmin, double *ymin, double *resolution);
+/* the best particle's distance field (GridMapper Cell::occ_dist, row-major i * xsize + j as grid_mapper.cpp:890-898)
+ * as fp32 written to a DEVICE buffer of `count` floats on the same GPU - e.g. the one returned by
+ * b2n_mppi_obstacle_field_device: the filter's map becomes the controller's obstacle term without touching the host.
+ * Synchronous: the field is complete at return. */
+int b2n_pf_write_distance_field(b2n_pf *h, float *device_out, size_t count);
 int b2n_pf_launch_count(const b2n_pf *h, uint64_t *launches);
 /* CUDA-event durations (ms) of the last SLAM(): [0] sample + weight + ray integration, [1] distance field,
  * [2] normalise + resample + particle copies */

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "b2n_mppi_set_plan": (C.c_int, [_vp, _vp, _sz]),
     "b2n_mppi_get_partials": (C.c_int, [_vp, _vp, _sz]),
     "b2n_mppi_set_obstacle_field": (C.c_int, [_vp, _vp, C.c_int, C.c_int, D, D, D, D, D, D]),
+    "b2n_mppi_obstacle_field_device": (C.c_int, [_vp, C.c_int, C.c_int, D, D, D, D, D, D, _P(_vp)]),
     "b2n_mppi_set_stream": (C.c_int, [_vp, _vp]),
     "b2n_mppi_set_state_ring": (C.c_int, [_vp, C.c_int]),
     "b2n_mppi_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
@@ -99,6 +100,8 @@ PROTOTYPES = {
     "b2n_pf_likelihoods": (C.c_int, [_vp, _vp, C.c_int, _vp, _sz]),
     "b2n_pf_normalize_resample": (C.c_int, [_vp]),
     "b2n_pf_set_stream": (C.c_int, [_vp, _vp]),
+    "b2n_pf_geometry": (C.c_int, [_vp, _P(D), _P(D), _P(D)]),
+    "b2n_pf_write_distance_field": (C.c_int, [_vp, _vp, _sz]),
     "b2n_pf_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "b2n_pf_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "b2n_pf_kernel_times": (C.c_int, [_vp, _P(D)]),

@@ -121,6 +121,15 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_set_obstacle_field(self._h, _capi.as_ptr(dist), xs, ys, xmin, ymin, resolution,
                                                           weight, d0, off_map))
 
+    def obstacleFieldFrom(self, pf, weight, d0, off_map):
+        """the filter's best map becomes the obstacle term, device to device (pf: bmapping.ParticleFilter)"""
+        xmin, ymin, res = C.c_double(), C.c_double(), C.c_double()
+        _capi.check(self._lib.b2n_pf_geometry(pf._h, C.byref(xmin), C.byref(ymin), C.byref(res)))
+        dev = C.c_void_p()
+        _capi.check(self._lib.b2n_mppi_obstacle_field_device(self._h, pf.xsize, pf.ysize, xmin.value, ymin.value, res.value, weight, d0,
+                                                             off_map, C.byref(dev)))
+        _capi.check(self._lib.b2n_pf_write_distance_field(pf._h, dev, pf.cells))
+
     def setStream(self, cuda_stream):
         _capi.check(self._lib.b2n_mppi_set_stream(self._h, C.c_void_p(cuda_stream)))
 

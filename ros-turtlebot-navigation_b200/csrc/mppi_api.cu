@@ -560,6 +560,25 @@ int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int y
   return B2N_OK;
 }
 
+int b2n_mppi_obstacle_field_device(b2n_mppi *h, int xsize, int ysize, double xmin, double ymin, double resolution, double weight,
+                                   double d0, double off_map, float **device_field)
+{
+  B2N_REQUIRE(h && device_field, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(xsize > 0 && ysize > 0 && resolution > 0.0, B2N_ERR_INVALID_ARGUMENT, "bad obstacle field geometry");
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)xsize * ysize;
+  if (!h->d_obs || (size_t)h->obs_xsize * h->obs_ysize != n) {
+    cudaFree(h->d_obs); h->d_obs = nullptr;
+    B2N_CUDA(cudaMalloc(&h->d_obs, n * sizeof(float)));
+    B2N_CUDA(cudaMemset(h->d_obs, 0x7f, n * sizeof(float)));     // ~3.4e38: no obstacle anywhere until the producer writes
+  }
+  h->obs_on = 1; h->obs_xsize = xsize; h->obs_ysize = ysize; h->obs_xmin = xmin; h->obs_ymin = ymin;
+  h->obs_res = resolution; h->obs_weight = weight; h->obs_d0 = d0; h->obs_off = off_map;
+  *device_field = h->d_obs;
+  return B2N_OK;
+}
+
 int b2n_mppi_set_stream(b2n_mppi *h, void *cuda_stream)
 {
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");

@@ -885,6 +885,29 @@ int b2n_pf_set_stream(b2n_pf *h, void *cuda_stream)
   return B2N_OK;
 }
 
+int b2n_pf_geometry(const b2n_pf *h, double *xmin, double *ymin, double *resolution)
+{
+  B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
+  if (xmin) *xmin = h->c.xmin;
+  if (ymin) *ymin = h->c.ymin;
+  if (resolution) *resolution = h->c.res;
+  return B2N_OK;
+}
+
+int b2n_pf_write_distance_field(b2n_pf *h, float *device_out, size_t count)
+{
+  B2N_REQUIRE(h && device_out, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(count == (size_t)h->c.G, B2N_ERR_INVALID_ARGUMENT, "count %zu, expected %d cells", count, h->c.G);
+  B2N_REQUIRE(h->nranks == 1, B2N_ERR_UNSUPPORTED, "single-rank operation (the best particle may live on another GPU)");
+  if (int rc = set_device(h)) return rc;
+  if (int rc = run_best(h)) return rc;
+  rbpf_export_distance_kernel<<<(h->c.G + 255) / 256, 256, 0, h->stream>>>(h->c, h->set[h->cur].d2, h->d_status + 3, h->max_occ_dist, device_out);
+  B2N_CUDA(cudaGetLastError());
+  h->launches++;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  return B2N_OK;
+}
+
 int b2n_pf_launch_count(const b2n_pf *h, uint64_t *launches)
 {
   B2N_REQUIRE(h && launches, B2N_ERR_INVALID_ARGUMENT, "null argument");

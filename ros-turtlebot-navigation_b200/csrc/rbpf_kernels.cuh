@@ -1176,6 +1176,16 @@ __global__ void __launch_bounds__(1024) rbpf_best_kernel(const PfParticle *meta,
   }
 }
 
+// distance field of one particle as fp32 metres (Cell::occ_dist = sqrt(d2) * resolution, max_occ_dist where never reached)
+__global__ void rbpf_export_distance_kernel(const __grid_constant__ PfConst c, const uint32_t *d2, const int *which, double max_occ_dist,
+                                            float *out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.G) return;
+  const uint32_t v = d2[(size_t)(*which) * c.gstride + i];
+  out[i] = (float)(v == kD2Unreached ? max_occ_dist : sqrt((double)v) * c.res);
+}
+
 // occupancy export of one particle: prob from the log-odds exactly as updateCellState left it, transposed output
 __global__ void rbpf_export_map_kernel(const __grid_constant__ PfConst c, const double *log_odds, const int *which, int8_t *out)
 {

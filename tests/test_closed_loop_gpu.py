@@ -63,3 +63,44 @@ def test_rbpf_feeds_mppi_closed_loop(gpu_pkg):
         assert np.array_equal(f.newMap(), of.new_map())
         est = tuple(want)
     assert resampled >= 1
+
+
+def test_filter_map_feeds_the_obstacle_term_on_the_device(gpu_pkg):
+    """SURVEY.md 8f row 4: the best particle's distance field goes device-to-device into the controller's obstacle term;
+    the oracle gets the same field through the host."""
+    pkg = gpu_pkg
+    N, K, hor, dt = 24, 1024, 0.64, 0.01
+    poses, twists = orc.circle_path(3)
+    rng = np.random.default_rng(8)
+    q = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3))
+    f = pkg.bmapping.make_filter(orc.pf_params(**q))
+    f.seed(2)
+    for i in range(3):
+        f.SLAM(orc.room_scan(poses[i + 1], rng=rng), pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
+    prm = orc.SHIPPED
+    m = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]), prm["lambda_"],
+                 prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], hor, dt, K)
+    m.obstacleFieldFrom(f, 5e4, 0.4, 1e6)
+    # the same field for the oracle: best particle = first maximum of the weights (particle_filter.cpp:255-274)
+    best = int(np.argmax(f.weights()))
+    dist = f.grid(best)["occ_dist"].astype(np.float32).reshape(f.xsize, f.ysize)
+    o = orc.OracleMppi(hor, dt, K)
+    o.set_obstacles(dist, -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+    m.setCapture(True)
+    m.seed(4)
+    o.noise_philox(4)
+    th, x, y = poses[3]
+    m.setWaypoint(pkg.Pose(theta=0.0, x=2.2, y=0.2))        # towards the box and the wall: the term is active
+    o.setWaypoint(2.2, 0.2, 0.0)
+    v = m.newControls(pkg.Pose(theta=th, x=x, y=y))
+    c = o.newControls(x, y, th)
+    g = o.get()
+    J = m.costToGo()
+    assert np.max(np.abs(J - g["J"].T) / np.maximum(np.abs(g["J"].T), 1e-6)) < 1e-11
+    assert max(abs(v.ul - c[0]), abs(v.ur - c[1])) / max(1e-3, abs(c[0]), abs(c[1])) < 1e-5
+    # and the term really bites: the same call without it costs less somewhere
+    o2 = orc.OracleMppi(hor, dt, K)
+    o2.noise_philox(4)
+    o2.setWaypoint(2.2, 0.2, 0.0)
+    o2.newControls(x, y, th)
+    assert np.max(g["J"] - o2.get()["J"]) > 1.0
