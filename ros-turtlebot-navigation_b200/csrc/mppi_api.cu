@@ -18,7 +18,7 @@ using namespace b2n;
 struct b2n_mppi
 {
   b2n_mppi_params p;
-  int T = 0, K = 0, S = 4, G = 16, device = 0;
+  int T = 0, K = 0, S = 4, G = 16, NW = 8, device = 0;
   double plan_abs_max = 0.0;             // bound on |u| over the plan, the tail value and the clamp
   bool force_generic = false;            // B2N_MPPI_GENERIC=1: never take the FAST rollout variant (tests)
   int n_sm = 0, grid = 0;
@@ -77,35 +77,37 @@ struct b2n_mppi
 namespace
 {
 
-// (S, G) = steps per lane, lanes per rollout; G * S >= T.  The table below is every shape that is built.
-template <int S, int G>
+// (S, G, NW) = steps per lane, lanes per rollout, warps per CTA; G * S >= T.  The table below is every shape that is built.
+template <int S, int G, int NW>
 cudaError_t configure_shape(b2n_mppi *h)
 {
-  h->smem = mppi_rollout_smem(S, G);
-  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  h->smem = mppi_rollout_smem(S, G, NW);
+  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0, per_sm_fast = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false>, kMppiThreads, h->smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false, NW>, NW * 32, h->smem);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, mppi_rollout_kernel<S, G, true>, kMppiThreads, h->smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, mppi_rollout_kernel<S, G, true, NW>, NW * 32, h->smem);
   if (e != cudaSuccess) return e;
   per_sm = std::max(per_sm, per_sm_fast);     // the partials buffer is sized for the larger grid; both variants stride by gridDim
   if (per_sm < 1) per_sm = 1;
   // persistent grid: every SM filled to its residency limit (an evenly divided but smaller grid measured slower:
   // SMs holding one CTA more than their neighbours set the pace)
-  const int per_cta = kMppiWarps * (32 / G);
+  const int per_cta = NW * (32 / G);
   const int want = (h->K + per_cta - 1) / per_cta;
   h->grid = std::max(1, std::min(want, per_sm * h->n_sm));
   return cudaSuccess;
 }
 
-#define B2N_MPPI_SHAPES(X) X(2, 8) X(4, 8) X(2, 16) X(4, 16) X(2, 32) X(4, 32) X(8, 32)
+// (7-warp CTAs, four per SM, divide K = 16384 into equal passes - measured no faster than 8-warp CTAs (22.2 vs 20.5 us):
+// the kernel is bound by the dependent instruction stream of a pass, not by the half-empty last pass; not instantiated)
+#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8)
 
 cudaError_t configure(b2n_mppi *h)
 {
-#define X(S_, G_) if (h->S == S_ && h->G == G_) return configure_shape<S_, G_>(h);
+#define X(S_, G_, W_) if (h->S == S_ && h->G == G_ && h->NW == W_) return configure_shape<S_, G_, W_>(h);
   B2N_MPPI_SHAPES(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -113,29 +115,31 @@ cudaError_t configure(b2n_mppi *h)
 
 void launch_rollout(b2n_mppi *h, const MppiArgs &a, bool fast)
 {
-#define X(S_, G_)                                                                                          \
-  if (h->S == S_ && h->G == G_) {                                                                          \
-    if (fast) mppi_rollout_kernel<S_, G_, true><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);          \
-    else mppi_rollout_kernel<S_, G_, false><<<h->grid, kMppiThreads, h->smem, h->stream>>>(a);              \
-    return;                                                                                                \
+#define X(S_, G_, W_)                                                                                           \
+  if (h->S == S_ && h->G == G_ && h->NW == W_) {                                                                \
+    if (fast) mppi_rollout_kernel<S_, G_, true, W_><<<h->grid, W_ * 32, h->smem, h->stream>>>(a);               \
+    else mppi_rollout_kernel<S_, G_, false, W_><<<h->grid, W_ * 32, h->smem, h->stream>>>(a);                   \
+    return;                                                                                                     \
   }
   B2N_MPPI_SHAPES(X)
 #undef X
 }
 
 // default shape: four steps per lane where the horizon allows it (fewest scan levels per step without running out
-// of registers); B2N_MPPI_SHAPE="S,G" overrides it for tuning runs
-void pick_shape(int T, int &S, int &G)
+// of registers), 8 warps per CTA; B2N_MPPI_SHAPE="S,G[,NW]" overrides it for tuning runs
+void pick_shape(int T, int &S, int &G, int &NW)
 {
+  NW = 8;
   if (T <= 16) { S = 2; G = 8; }
   else if (T <= 32) { S = 4; G = 8; }
   else if (T <= 64) { S = 4; G = 16; }
   else if (T <= 128) { S = 4; G = 32; }
   else { S = 8; G = 32; }
   if (const char *env = std::getenv("B2N_MPPI_SHAPE")) {
-    int s = 0, g = 0;
-    if (std::sscanf(env, "%d,%d", &s, &g) == 2 && s * g >= T) {
-#define X(S_, G_) if (s == S_ && g == G_) { S = s; G = g; }
+    int s = 0, g = 0, w = 8;
+    const int n = std::sscanf(env, "%d,%d,%d", &s, &g, &w);
+    if (n >= 2 && s * g >= T) {
+#define X(S_, G_, W_) if (s == S_ && g == G_ && w == W_) { S = s; G = g; NW = w; }
       B2N_MPPI_SHAPES(X)
 #undef X
     }
@@ -304,7 +308,7 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   h->p = p;
   h->T = T;
   h->K = p.rollouts;
-  pick_shape(T, h->S, h->G);
+  pick_shape(T, h->S, h->G, h->NW);
   h->plan_abs_max = std::fabs(p.max_wheel_vel);   // the plan starts at 0 and every update is clamped to +-max_wheel_vel
   if (const char *env = std::getenv("B2N_MPPI_GENERIC")) h->force_generic = env[0] == '1';
   if (p.device >= 0) h->device = p.device; else cudaGetDevice(&h->device);

@@ -110,16 +110,18 @@ __device__ __forceinline__ void mppi_sincos_small(double d, double &sn, double &
 
 // dynamic shared memory: [warps][2][32*S*3] fp32 staging rows, then [S*6][threads] fp64 online-softmax accumulators
 // (kept out of the register file so that three CTAs fit an SM; reused as [warps][G*S][6] for the CTA merge)
-__host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G)
+__host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW)
 {
-  return (size_t)kMppiWarps * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * kMppiThreads * sizeof(double);
+  return (size_t)NW * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * NW * 32 * sizeof(double);
 }
 
 // FAST = the production configuration, decided on the host: own noise, no capture taps, no obstacle term, T == G * S
 // (no partially filled lanes), TMA row stores, and half-step heading increments provably inside the Taylor range.
-template <int S, int G, bool FAST>
-__global__ void __launch_bounds__(kMppiThreads, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+// NW = warps per CTA: 8, or 7 (four CTAs = 28 warps per SM) where that divides the job into equal passes.
+template <int S, int G, bool FAST, int NW>
+__global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
 {
+  constexpr int kMppiWarps = NW, kMppiThreads = NW * 32;     // shadow the defaults: every layout below follows the CTA shape
   static_assert(S % 2 == 0 && (G == 8 || G == 16 || G == 32), "a Philox call covers two steps; G lanes per rollout");
   constexpr int R = 32 / G;        // rollouts a warp carries at a time
   constexpr int TP = G * S;        // padded horizon

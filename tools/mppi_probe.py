@@ -16,11 +16,13 @@ dt = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
 params = sys.argv[4] if len(sys.argv) > 4 else "shipped"
 pkg = _pkg.load()
 prm = orc.SHIPPED if params == "shipped" else orc.MILD
-shapes = [(2, 8), (4, 8), (2, 16), (4, 16), (2, 32), (4, 32), (8, 32)]
+shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8)]
 if os.environ.get("PROBE_SHAPES"):
     shapes = [tuple(int(v) for v in x.split(",")) for x in os.environ["PROBE_SHAPES"].split(";")]
-for (S, G) in shapes:
-    os.environ["B2N_MPPI_SHAPE"] = "%d,%d" % (S, G)
+for shape in shapes:
+    S, G = shape[0], shape[1]
+    NW = shape[2] if len(shape) > 2 else 8
+    os.environ["B2N_MPPI_SHAPE"] = "%d,%d,%d" % (S, G, NW)
     m = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
                  prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], hor, dt, K)
     T = m.steps
@@ -43,6 +45,7 @@ for (S, G) in shapes:
         m.enqueue(pose)
     m.wait()
     kms, kn = m.kernelTime()
-    print("K=%d T=%d %s shape S=%d G=%d: %.2f us/call (%.3e traj-steps/s), rollout kernel %.2f us (events)"
-          % (K, T, params, S, G, el * 1e6, K * T / el, kms * 1e3), flush=True)
+    kms = m.timeRollout(pose, n)
+    print("K=%d T=%d %s shape S=%d G=%d NW=%d: %.2f us/call (%.3e traj-steps/s), rollout kernel %.2f us (back to back)"
+          % (K, T, params, S, G, NW, el * 1e6, K * T / el, kms * 1e3), flush=True)
     del m
