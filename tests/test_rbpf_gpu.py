@@ -227,3 +227,49 @@ def test_error_behaviour(gpu_pkg):
         g.setNoise(np.zeros(5))
     with pytest.raises(gpu_pkg.B2NError):
         slam_gpu(gpu_pkg, g, np.zeros(4000, dtype=np.float32), (0, 0, 0), (0, 0, 0), (0, 0, 0))
+
+
+@pytest.mark.parametrize("env", [{"B2N_PF_DF_LANES": "8"}, {"B2N_PF_DF_LANES": "16"}, {"B2N_PF_DF_LANES": "32"},
+                                 {"B2N_PF_DF_LANES": "32", "B2N_PF_DF_SMEM_MARKS": "1"}])
+def test_every_distance_field_kernel_variant_is_bit_exact(gpu_pkg, env, monkeypatch):
+    """The brushfire exists in four forms (lane groups of 8 / 16 with the visited bitmap in tensor memory staged through
+    shared memory, one particle per warp with the bitmap in tensor memory or in shared memory); the handle reads the choice
+    from the environment at creation.  All must reproduce the oracle's field, heap order quirks included."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    N, scans = 37, 4                                   # not a multiple of any group size
+    poses, twists = orc.circle_path(scans)
+    kw = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3))
+    f = make_gpu(gpu_pkg, **kw)
+    o = orc.OraclePf(**kw)
+    f.seed(3)
+    o.noise_philox(3)
+    for i in range(scans):
+        scan = orc.room_scan(poses[i + 1], rng=rng)
+        assert o.slam(scan, twists[i], poses[i + 1], poses[i]) == 0
+        slam_gpu(gpu_pkg, f, scan, twists[i], poses[i + 1], poses[i])
+        for k in (0, 17, N - 1):
+            assert_grid_equal(f.grid(k), o.grid(k))
+    assert rel(f.weights(), o.state()["weights"]) < 1e-9
+
+
+def test_shipped_launch_map_80x80(gpu_pkg):
+    """bmapping/launch/slam.launch:40-42: a 4 m x 4 m map (80 x 80 cells) - another grid size, another bitmap width."""
+    rng = np.random.default_rng(5)
+    N, scans = 24, 4
+    poses, twists = orc.circle_path(scans, radius=0.3, step=0.04)
+    kw = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(1e-3, 5e-4, 5e-4), xmin=-2.0, xmax=2.0, ymin=-2.0, ymax=2.0)
+    f = make_gpu(gpu_pkg, **kw)
+    o = orc.OraclePf(**kw)
+    f.seed(8)
+    o.noise_philox(8)
+    for i in range(scans):
+        scan = orc.room_scan(poses[i + 1], half=1.6, boxes=((0.6, 0.9, -0.2, 0.3),), rng=rng)
+        assert o.slam(scan, twists[i], poses[i + 1], poses[i]) == 0
+        slam_gpu(gpu_pkg, f, scan, twists[i], poses[i + 1], poses[i])
+        assert np.array_equal(f.resampleInfo()[2], o.resample_info()[2])
+        for k in (0, N - 1):
+            assert_grid_equal(f.grid(k), o.grid(k))
+        assert np.array_equal(f.newMap(), o.new_map())
+    assert rel(f.weights(), o.state()["weights"]) < 1e-9
