@@ -169,7 +169,7 @@ def rbpf_cpu(kind, budget_s=12.0, n_particles=64):
                       % (done, n_particles, RBPF_N, el)}
 
 
-def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=None):
+def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=None, exchange="p2p"):
     """BASELINE configs[2]: RBPF 4096 particles (per GPU: weak scaling), 360-beam synthetic lidar, 200x200 map,
     motion-model branch: sample + beam weighting + ray integration + distance field + normalise + resample, every
     scan.  At N > 1 GPUs the weights travel with one allgather per scan, every rank runs the identical walk and
@@ -183,6 +183,11 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
             uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        if exchange == "p2p":
+            mine = torch.frombuffer(bytearray(f.p2pExport()), dtype=torch.uint8).cuda()
+            hs = [torch.zeros(640, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(hs, mine)
+            f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
     else:
         f = pkg.bmapping.make_filter(q, device=local)
     f.seed(1)
@@ -229,7 +234,7 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
         "config": {"workload": "RBPF 4096 particles per GPU, 360-beam synthetic lidar, 200x200 occupancy grid (BASELINE configs[2]), motion-model branch",
                    "particles_per_gpu": RBPF_N, "particles_total": n_all, "beams": RBPF_BEAMS, "cells": RBPF_CELLS, "scans": n_scans,
                    "warmup_scans": warmup, "resampled_scans": int(resampled), "particles_migrated_between_gpus": int(migrated),
-                   "sharding": "particles; weights allgather + identical walk + ncclSend/ncclRecv migration" if world > 1 else "none",
+                   "sharding": ("particles; weights allgather + identical walk + migration by %s" % ("peer-memory copy kernel over NVLink" if exchange == "p2p" else "ncclSend/ncclRecv")) if world > 1 else "none",
                    "l2": "per-particle planes total %.1f GB per GPU >> 126 MB L2" % (RBPF_N * RBPF_CELLS * 12 / 1e9)},
         "ms_per_scan": dev_ms / n_scans,
         "kernel_ms_per_scan": {"update(sample+weight+rays)": ms[0] / n_scans, "distance_field": df_ms,
@@ -430,7 +435,7 @@ def run_ours(args):
     rbpf = None
     if not args.no_rbpf:
         mppi.close()
-        rbpf = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3, rank, world, local, dist if world > 1 else None)
+        rbpf = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3, rank, world, local, dist if world > 1 else None, args.exchange)
     if rank == 0:
         if rbpf is not None:
             line["rbpf"] = rbpf

@@ -244,6 +244,12 @@ int b2n_pf_comm_init(b2n_pf *h, int rank, int nranks, const void *unique_id128);
  * the order the exchange posts them (ascending ancestor per peer). */
 int b2n_pf_plan_migration(const int32_t *ancestors, int n_total, int rank, int nranks, int32_t *copy1, int32_t *copy2, int32_t *recv,
                           size_t recv_cap, int *n_recv, int32_t *send, size_t send_cap, int *n_send);
+/* The same migration over NVLink peer memory instead of ncclSend/ncclRecv (ranks = processes on ONE node): every rank
+ * exports the CUDA IPC handles of its plane allocations (b2n_pf_p2p_export: 10 x 64 bytes), the caller gathers them in
+ * rank order (nranks x 640 bytes) and hands them to b2n_pf_p2p_init after b2n_pf_comm_init.  From then on a resampling
+ * step is ONE copy kernel in which every slot reads its ancestor where it lives - local HBM or a peer's. */
+int b2n_pf_p2p_export(b2n_pf *h, void *handles640);
+int b2n_pf_p2p_init(b2n_pf *h, int rank, int nranks, const void *handles);
 /* particles received from / sent to other ranks by the last SLAM() */
 int b2n_pf_get_migration(const b2n_pf *h, int *received, int *sent);
 

@@ -109,6 +109,8 @@ PROTOTYPES = {
     "b2n_pf_set_heap_capacity": (C.c_int, [_vp, C.c_int]),
     "b2n_pf_host_tables": (C.c_int, [_P(PfParams), _P(D), _vp, _sz, _vp, _sz, _P(C.c_int)]),
     "b2n_pf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b2n_pf_p2p_export": (C.c_int, [_vp, _vp]),
+    "b2n_pf_p2p_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2n_pf_plan_migration": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _P(C.c_int), _vp, _sz, _P(C.c_int)]),
     "b2n_pf_get_migration": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int)]),
 }

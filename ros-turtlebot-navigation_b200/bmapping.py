@@ -198,6 +198,17 @@ class ParticleFilter:
     def setHeapCapacity(self, entries):
         _capi.check(self._lib.b2n_pf_set_heap_capacity(self._h, int(entries)))
 
+    def p2pExport(self):
+        """the 640 bytes of CUDA IPC handles of this rank's planes, to hand to the other ranks"""
+        buf = C.create_string_buffer(640)
+        _capi.check(self._lib.b2n_pf_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2pInit(self, rank, nranks, handles):
+        """handles: nranks x 640 bytes, every rank's p2pExport() in rank order (after commInit)"""
+        buf = C.create_string_buffer(bytes(handles), 640 * int(nranks))
+        _capi.check(self._lib.b2n_pf_p2p_init(self._h, int(rank), int(nranks), buf))
+
     def migration(self):
         """(particles received from, sent to) other ranks by the last SLAM()"""
         a, b = C.c_int(), C.c_int()

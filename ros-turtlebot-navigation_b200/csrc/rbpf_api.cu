@@ -51,6 +51,10 @@ struct b2n_pf
   int8_t *d_map = nullptr;
   double *d_lik = nullptr;
   int32_t *d_idx = nullptr;           // [2][N] copy lists of a cross-rank resampling
+  // peer-memory migration (CUDA IPC): every rank's plane allocations of both sets mapped into this process
+  bool p2p_ready = false;
+  std::vector<void *> peer_ptrs;      // [nranks][2 sets][5 planes], own entries = own pointers
+  PfPlanes *d_peer_sets = nullptr;    // device: [2 sets][nranks]
   int last_migrated_in = 0, last_migrated_out = 0;
 
   uint64_t seed = 0;
@@ -351,6 +355,18 @@ void host_tables(const b2n_pf_params &p, int xsize, int ysize, long long G, int 
 int migrate_particles(b2n_pf *h, const PfPlanes &src, const PfPlanes &dst)
 {
   const PfConst &c = h->c;
+  if (h->p2p_ready) {
+    // every slot reads its ancestor where it lives: local HBM or a peer's HBM over NVLink; the allgather of the weights
+    // that preceded the walk is the barrier that makes every rank's old set final, the next one protects it from reuse
+    int in = 0;
+    for (int m = 0; m < h->N; m++) in += (h->h_anc[h->offset + m] / h->N) != h->rank;
+    h->last_migrated_in = in; h->last_migrated_out = 0;
+    dim3 grid(8, h->N);
+    rbpf_copy_particles_p2p_kernel<<<grid, 256, 0, h->stream>>>(c, h->d_peer_sets + (size_t)h->cur * h->nranks, dst, h->d_anc, h->offset, h->N, h->d_w);
+    B2N_CUDA(cudaGetLastError());
+    h->launches++;
+    return B2N_OK;
+  }
   MigrationPlan mp;
   plan_migration(h->h_anc.data(), h->n_total, h->N, h->rank, h->nranks, mp);
   if (!h->d_idx) B2N_CUDA(cudaMalloc(&h->d_idx, sizeof(int32_t) * 2 * (size_t)h->N));
@@ -526,6 +542,13 @@ void b2n_pf_destroy(b2n_pf *h)
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) ncclCommDestroy(h->comm);
+  if (h->p2p_ready) {
+    for (int r = 0; r < h->nranks; r++)
+      if (r != h->rank)
+        for (int k = 0; k < 10; k++)
+          if (h->peer_ptrs[(size_t)r * 10 + k]) cudaIpcCloseMemHandle(h->peer_ptrs[(size_t)r * 10 + k]);
+  }
+  cudaFree(h->d_peer_sets);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   free_planes(h->set[0]); free_planes(h->set[1]);
   cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_w); cudaFree(h->d_anc);
@@ -1000,6 +1023,60 @@ int b2n_pf_get_migration(const b2n_pf *h, int *received, int *sent)
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
   if (received) *received = h->last_migrated_in;
   if (sent) *sent = h->last_migrated_out;
+  return B2N_OK;
+}
+
+int b2n_pf_p2p_export(b2n_pf *h, void *handles640)
+{
+  B2N_REQUIRE(h && handles640, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  char *out = static_cast<char *>(handles640);
+  for (int s = 0; s < 2; s++) {
+    void *planes[5] = {h->set[s].log_odds, h->set[s].d2, h->set[s].nxt, h->set[s].bkt, h->set[s].meta};
+    for (int k = 0; k < 5; k++) {
+      cudaIpcMemHandle_t ipc;
+      B2N_CUDA(cudaIpcGetMemHandle(&ipc, planes[k]));
+      std::memcpy(out + (size_t)(s * 5 + k) * sizeof(ipc), &ipc, sizeof(ipc));
+    }
+  }
+  return B2N_OK;
+}
+
+int b2n_pf_p2p_init(b2n_pf *h, int rank, int nranks, const void *handles)
+{
+  B2N_REQUIRE(h && handles, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->comm && rank == h->rank && nranks == h->nranks, B2N_ERR_INVALID_ARGUMENT,
+              "b2n_pf_comm_init comes first (the weights still travel with ncclAllGather), with the same rank and size");
+  if (int rc = set_device(h)) return rc;
+  h->peer_ptrs.assign((size_t)nranks * 10, nullptr);
+  std::vector<PfPlanes> sets((size_t)2 * nranks);
+  for (int r = 0; r < nranks; r++) {
+    for (int s = 0; s < 2; s++) {
+      void *p[5];
+      if (r == rank) {
+        p[0] = h->set[s].log_odds; p[1] = h->set[s].d2; p[2] = h->set[s].nxt; p[3] = h->set[s].bkt; p[4] = h->set[s].meta;
+      } else {
+        for (int k = 0; k < 5; k++) {
+          cudaIpcMemHandle_t ipc;
+          std::memcpy(&ipc, static_cast<const char *>(handles) + ((size_t)r * 10 + s * 5 + k) * sizeof(ipc), sizeof(ipc));
+          cudaError_t e = cudaIpcOpenMemHandle(&p[k], ipc, cudaIpcMemLazyEnablePeerAccess);
+          if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaIpcOpenMemHandle for rank %d: %s (peer access between the GPUs is required)", r, cudaGetErrorString(e));
+            return B2N_ERR_COMM;
+          }
+        }
+      }
+      for (int k = 0; k < 5; k++) h->peer_ptrs[(size_t)r * 10 + s * 5 + k] = p[k];
+      PfPlanes &q = sets[(size_t)s * nranks + r];
+      q.log_odds = static_cast<double *>(p[0]); q.d2 = static_cast<uint32_t *>(p[1]); q.nxt = static_cast<uint16_t *>(p[2]);
+      q.bkt = static_cast<uint16_t *>(p[3]); q.meta = static_cast<PfParticle *>(p[4]);
+    }
+  }
+  if (!h->d_peer_sets) B2N_CUDA(cudaMalloc(&h->d_peer_sets, sets.size() * sizeof(PfPlanes)));
+  B2N_CUDA(cudaMemcpy(h->d_peer_sets, sets.data(), sets.size() * sizeof(PfPlanes), cudaMemcpyHostToDevice));
+  h->p2p_ready = true;
   return B2N_OK;
 }
 

@@ -1140,6 +1140,39 @@ __global__ void __launch_bounds__(256) rbpf_copy_particles_kernel(const __grid_c
   if (tid == 0) dst.meta[m] = src.meta[a];
 }
 
+// Resampling across GPUs over NVLink peer memory: slot m of dst <- particle src_index[m] of rank src_rank[m], read straight
+// out of that rank's planes (mapped with CUDA IPC; sets[r] = rank r's OLD set, the own rank included, so local and
+// remote ancestors are one code path and one launch).  The copied particle's weight is taken from the normalised global
+// weight vector every rank holds after the allgather - the remote meta may not have received it yet.
+__global__ void __launch_bounds__(256) rbpf_copy_particles_p2p_kernel(const __grid_constant__ PfConst c, const PfPlanes *sets, const PfPlanes dst,
+                                                                       const int32_t *ancestors, int slot_offset, int n_local, const double *w_all)
+{
+  const int m = blockIdx.y;
+  const int ga = ancestors[slot_offset + m];                 // global ancestor
+  const PfPlanes src = sets[ga / n_local];
+  const int a = ga % n_local;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const uint4 *s0 = reinterpret_cast<const uint4 *>(src.log_odds + (size_t)a * c.gstride);
+  uint4 *d0 = reinterpret_cast<uint4 *>(dst.log_odds + (size_t)m * c.gstride);
+  for (int i = tid; i < c.gstride / 2; i += nth) d0[i] = s0[i];
+  const uint4 *s1 = reinterpret_cast<const uint4 *>(src.d2 + (size_t)a * c.gstride);
+  uint4 *d1 = reinterpret_cast<uint4 *>(dst.d2 + (size_t)m * c.gstride);
+  for (int i = tid; i < c.gstride / 4; i += nth) d1[i] = s1[i];
+  const uint4 *s2 = reinterpret_cast<const uint4 *>(src.nxt + (size_t)a * c.nxt_stride);
+  uint4 *d2 = reinterpret_cast<uint4 *>(dst.nxt + (size_t)m * c.nxt_stride);
+  for (int i = tid; i < c.nxt_stride / 8; i += nth) d2[i] = s2[i];
+  const PfParticle meta = src.meta[a];
+  const int used = (int)((meta.bucket_count + 7) / 8);
+  const uint4 *s3 = reinterpret_cast<const uint4 *>(src.bkt + (size_t)a * c.bkt_stride);
+  uint4 *d3 = reinterpret_cast<uint4 *>(dst.bkt + (size_t)m * c.bkt_stride);
+  for (int i = tid; i < used; i += nth) d3[i] = s3[i];
+  if (tid == 0) {
+    PfParticle q = meta;
+    q.weight = w_all[ga];
+    dst.meta[m] = q;
+  }
+}
+
 // ---- getRobotState / newMap (particle_filter.cpp:255-291, grid_mapper.cpp:185-226) ----------------------------------
 // first particle with the largest weight, strict > starting from 0.0 (so index 0 when nothing is positive)
 __global__ void __launch_bounds__(1024) rbpf_best_kernel(const PfParticle *meta, int n, int *best, double *best_pose_weight)

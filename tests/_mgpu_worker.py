@@ -70,46 +70,53 @@ def main():
         m.close()
 
     # ---- RBPF: N particles over `world` ranks: weights allgather, identical walk, migration -----------------------
-    # a second communicator id for the filter handle
-    uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid2.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid2, 0)
     N, scans = 64, 6
     Nl = N // world
     poses, twists = orc.circle_path(scans)
-    rng = np.random.default_rng(5)
     q = dict(init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3))
-    f = pkg.bmapping.make_filter(orc.pf_params(num_particles=Nl, **q), particle_offset=rank * Nl, particles_total=N, device=local)
-    f.commInit(rank, world, bytes(uid2.cpu().numpy().tobytes()))
-    f.seed(3)
-    of = orc.OraclePf(num_particles=N, **q)
-    of.noise_philox(3)
-    res = {"weights": 0.0, "poses": 0.0, "ancestors_equal": True, "resampled": 0, "map_equal": True, "migrated": 0}
-    for i in range(scans):
-        scan = orc.room_scan(poses[i + 1], rng=rng)
-        f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
-        of.slam(scan, twists[i], poses[i + 1], poses[i])
-        st = of.state()
-        neff, rs, anc = f.resampleInfo()
-        oneff, ors, oanc = of.resample_info()
-        res["resampled"] += rs
-        res["ancestors_equal"] &= bool(rs == ors and neff == oneff and np.array_equal(anc, oanc))
-        sl = slice(rank * Nl, (rank + 1) * Nl)
-        w = f.weights()
-        res["weights"] = max(res["weights"], float(np.max(np.abs(w - st["weights"][sl]) / np.maximum(np.abs(st["weights"][sl]), 1e-300))))
-        p, _ = f.poses()
-        res["poses"] = max(res["poses"], float(np.max(np.abs(p - st["poses"][sl]))))
-        for j in (0, Nl - 1):                                   # first and last local particle: full map, bit for bit
-            gg, go = f.grid(j), of.grid(rank * Nl + j)
-            res["map_equal"] &= bool(np.array_equal(gg["log_odds"], go["log_odds"]) and np.array_equal(gg["occ_dist"], go["occ_dist"]))
-        res["migrated"] += f.migration()[0]
-    out["rbpf"] = res
+    for mode in ("nccl", "p2p"):
+        uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid2.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid2, 0)
+        rng = np.random.default_rng(5)
+        f = pkg.bmapping.make_filter(orc.pf_params(num_particles=Nl, **q), particle_offset=rank * Nl, particles_total=N, device=local)
+        f.commInit(rank, world, bytes(uid2.cpu().numpy().tobytes()))
+        if mode == "p2p":
+            mine = torch.frombuffer(bytearray(f.p2pExport()), dtype=torch.uint8).cuda()
+            hs = [torch.zeros(640, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(hs, mine)
+            f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+        f.seed(3)
+        of = orc.OraclePf(num_particles=N, **q)
+        of.noise_philox(3)
+        res = {"weights": 0.0, "poses": 0.0, "ancestors_equal": True, "resampled": 0, "map_equal": True, "migrated": 0}
+        for i in range(scans):
+            scan = orc.room_scan(poses[i + 1], rng=rng)
+            f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
+            of.slam(scan, twists[i], poses[i + 1], poses[i])
+            st = of.state()
+            neff, rs, anc = f.resampleInfo()
+            oneff, ors, oanc = of.resample_info()
+            res["resampled"] += rs
+            res["ancestors_equal"] &= bool(rs == ors and neff == oneff and np.array_equal(anc, oanc))
+            sl = slice(rank * Nl, (rank + 1) * Nl)
+            w = f.weights()
+            res["weights"] = max(res["weights"], float(np.max(np.abs(w - st["weights"][sl]) / np.maximum(np.abs(st["weights"][sl]), 1e-300))))
+            p, _ = f.poses()
+            res["poses"] = max(res["poses"], float(np.max(np.abs(p - st["poses"][sl]))))
+            for j in (0, Nl // 2, Nl - 1):                          # full maps, bit for bit
+                gg, go = f.grid(j), of.grid(rank * Nl + j)
+                res["map_equal"] &= bool(np.array_equal(gg["log_odds"], go["log_odds"]) and np.array_equal(gg["occ_dist"], go["occ_dist"]))
+                res["map_equal"] &= bool(np.array_equal(f.occOrder(j), of.occ_order(rank * Nl + j)))
+            res["migrated"] += f.migration()[0]
+        out["rbpf_" + mode] = res
+        dist.barrier()
+        f.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(gathered), flush=True)
-    f.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -22,8 +22,10 @@ def test_two_gpus_match_the_unsharded_oracle(gpu_pkg):
         for mode in ("mppi_nccl", "mppi_p2p"):
             assert res[mode]["controls_rel_err"] < 1e-5 and res[mode]["plan_rel_err"] < 1e-5, (mode, res[mode])
             assert res[mode]["plan_replicated_bitwise"], mode       # identical update on every rank, no broadcast
-        rb = res["rbpf"]
-        assert rb["ancestors_equal"] and rb["map_equal"]          # resampling indices and maps bit-exact
-        assert rb["weights"] < 1e-9 and rb["poses"] < 1e-9
-        assert rb["resampled"] >= 1
-    assert sum(res["rbpf"]["migrated"] for res in json.loads(line[len("MGPU_RESULT "):])) >= 1   # particles really changed GPU
+        for mode in ("rbpf_nccl", "rbpf_p2p"):
+            rb = res[mode]
+            assert rb["ancestors_equal"] and rb["map_equal"], mode      # resampling indices and maps bit-exact
+            assert rb["weights"] < 1e-9 and rb["poses"] < 1e-9, mode
+            assert rb["resampled"] >= 1
+    for mode in ("rbpf_nccl", "rbpf_p2p"):
+        assert sum(res[mode]["migrated"] for res in json.loads(line[len("MGPU_RESULT "):])) >= 1   # particles really changed GPU
