@@ -341,7 +341,11 @@ def run_ours(args):
             hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(hs, mine)
             mppi.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
-    stream = torch.cuda.current_stream()
+    # the handle launches on THIS stream and the timing events are recorded on it (torch's current stream is the
+    # legacy default stream, handle 0, which b2n_mppi_set_stream reads as "use your own": events there would bracket
+    # nothing but the host's enqueue loop)
+    stream = torch.cuda.Stream(device=local)
+    assert stream.cuda_stream != 0
     mppi.setStream(stream.cuda_stream)
     mppi.setStateRing(STATE_RING)
     mppi.seed(42)

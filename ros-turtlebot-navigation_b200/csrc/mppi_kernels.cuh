@@ -130,9 +130,6 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
   double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
   double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4);             // [warps][TP][6] (epilogue)
 
-  // let a programmatically dependent grid (the update kernel) be scheduled as soon as this grid frees resources;
-  // it blocks in griddepcontrol.wait until this grid has completed
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = lane & (G - 1);    // position inside the rollout's lane group
@@ -156,6 +153,9 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
     for (int j = 1; j < 6; j++) acc[(s * 6 + j) * kMppiThreads] = 0.0;
   }
 
+  // launched programmatically dependent on the previous call's update kernel: everything above overlapped its tail;
+  // the plan it writes is read from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int buf = 0;
   for (int base = gw * R; base < a.K; base += nw * R, buf ^= 1) {
     const int k = base + r;
@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
       __syncwarp();
     }
   }
+  // the rollouts are done: let the dependent grid (the update kernel) be scheduled while this CTA merges; it blocks in
+  // griddepcontrol.wait until this whole grid has completed and its partials are visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tma_store && lane == 0) tma_store_wait<0>();
 
   // ---- merge the CTA's accumulator sets per time step: minimum first, then every set rescaled ONCE -----------------
@@ -397,29 +400,49 @@ constexpr int kMppiUpdateThreads = 128;
 __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int T, int t, double inv_lambda, double &m,
                                                  double &S, double &A, double &B, double &DL, double &DR)
 {
+  constexpr int kPer = 4;                                   // partials held in registers per thread (one L2 round trip)
   __shared__ double red[kMppiUpdateThreads / 32][6];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  double2 c0[kPer], c1[kPer], c2[kPer];
   m = inf;
-  for (int p = threadIdx.x; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, partials[((size_t)p * T + t) * 6]);
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    const int p = threadIdx.x + i * kMppiUpdateThreads;
+    c0[i] = make_double2(inf, 0.0); c1[i] = make_double2(0.0, 0.0); c2[i] = make_double2(0.0, 0.0);
+    if (p < n_partials) {
+      const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
+      c0[i] = c[0]; c1[i] = c[1]; c2[i] = c[2];
+    }
+    m = fmin(m, c0[i].x);
+  }
+  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, partials[((size_t)p * T + t) * 6]);
   m = warp_min(m);
   if (lane == 0) red[warp][0] = m;
   __syncthreads();
   m = red[0][0];
 #pragma unroll
   for (int w = 1; w < kMppiUpdateThreads / 32; w++) m = fmin(m, red[w][0]);
-  __syncthreads();
   S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
-  for (int p = threadIdx.x; p < n_partials; p += kMppiUpdateThreads) {
-    const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
-    const double2 c0 = c[0], c1 = c[1], c2 = c[2];
-    if (c0.x != inf) {
-      const double f = (c0.x == m) ? 1.0 : mppi_exp_neg((m - c0.x) * inv_lambda);
-      S = fma(c0.y, f, S); A = fma(c1.x, f, A); B = fma(c1.y, f, B);
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    if (c0[i].x != inf) {
+      const double f = (c0[i].x == m) ? 1.0 : mppi_exp_neg((m - c0[i].x) * inv_lambda);
+      S = fma(c0[i].y, f, S); A = fma(c1[i].x, f, A); B = fma(c1[i].y, f, B);
     }
-    DL += c2.x; DR += c2.y;
+    DL += c2[i].x; DR += c2[i].y;
+  }
+  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) {
+    const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
+    const double2 d0 = c[0], d1 = c[1], d2 = c[2];
+    if (d0.x != inf) {
+      const double f = (d0.x == m) ? 1.0 : mppi_exp_neg((m - d0.x) * inv_lambda);
+      S = fma(d0.y, f, S); A = fma(d1.x, f, A); B = fma(d1.y, f, B);
+    }
+    DL += d2.x; DR += d2.y;
   }
   S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
+  __syncthreads();
   if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -460,6 +483,8 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   // launched with programmatic stream serialization: wait here until the producing grid has finished and its
   // partials are visible (a no-op for an ordinary launch)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the next call's rollout grid may be scheduled now (its prologue overlaps this kernel; it waits before the plan)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
   mppi_block_merge(a.partials, a.n_partials, a.T, t, a.inv_lambda, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
@@ -496,6 +521,8 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kerne
   __shared__ double all[kMppiMaxRanks][6];
   const int t = blockIdx.x, T = a.T, j = threadIdx.x;
   const int par = (int)(x.call_id & 1ull);
+  asm volatile("griddepcontrol.wait;" ::: "memory");                 // programmatic dependent launch, as in mppi_update_kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
   mppi_block_merge(a.partials, a.n_partials, T, t, a.inv_lambda, m, S, A, B, DL, DR);
   if (j == 0) { mine[0] = m; mine[1] = S; mine[2] = A; mine[3] = B; mine[4] = DL; mine[5] = DR; }
