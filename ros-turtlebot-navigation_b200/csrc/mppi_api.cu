@@ -259,11 +259,11 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
     u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
     MppiXchgArgs xa;
     std::memset(&xa, 0, sizeof(xa));
-    for (int r = 0; r < h->nranks; r++) {
-      xa.peer_data[r] = static_cast<double *>(h->peer_base[r]);
-      xa.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->peer_base[r]) + h->xchg_flag_offset);
-    }
-    xa.rank = h->rank; xa.nranks = h->nranks; xa.call_id = ++h->xchg_call;
+    for (int r = 0; r < h->nranks; r++) xa.peer[r] = static_cast<unsigned long long *>(h->peer_base[r]);
+    xa.rank = h->rank; xa.nranks = h->nranks;
+    h->xchg_call++;
+    xa.parity = (int)(h->xchg_call & 1ull);
+    xa.call_id = (uint32_t)(h->xchg_call % 0xFFFFFFFFull) + 1u;
     {
       cudaLaunchConfig_t cfg;
       std::memset(&cfg, 0, sizeof(cfg));
@@ -696,9 +696,8 @@ int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64)
   B2N_REQUIRE(nranks >= 2 && nranks <= kMppiMaxRanks, B2N_ERR_INVALID_ARGUMENT, "nranks must be in [2, %d]", kMppiMaxRanks);
   B2N_REQUIRE(!h->xchg, B2N_ERR_INVALID_ARGUMENT, "exchange area already exported");
   if (int rc = set_device(h)) return rc;
-  const size_t slots = (size_t)2 * nranks * h->T;
-  h->xchg_flag_offset = slots * 6 * sizeof(double);
-  h->xchg_bytes = h->xchg_flag_offset + slots * sizeof(unsigned long long);
+  h->xchg_bytes = (size_t)2 * nranks * h->T * kMppiXchgWords * sizeof(unsigned long long);
+  h->xchg_flag_offset = 0;
   B2N_CUDA(cudaMalloc(&h->xchg, h->xchg_bytes));
   B2N_CUDA(cudaMemset(h->xchg, 0, h->xchg_bytes));
   h->xchg_nranks = nranks;

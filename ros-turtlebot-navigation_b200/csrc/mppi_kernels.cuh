@@ -497,70 +497,75 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
 }
 
 // ---- sharded rollouts: merge + exchange + update in ONE kernel over NVLink peer memory ----------------
-// Every rank owns an exchange area [2 call parities][nranks][T] x {6 doubles, flag}; peer[j] is rank j's area mapped
-// into this process (CUDA IPC).  CTA t merges this rank's CTA partials for step t, thread j stores the 48-byte result
-// straight into rank j's area (slot = this rank), fences at system scope and publishes the call id in the slot's
-// flag; it then spins on the flag of slot j in its OWN area and reads rank j's result.  Thread 0 folds the nranks
-// results in rank order (identical on every rank, so the plan stays replicated without a broadcast) and applies the
-// update.  No NCCL call, no extra launch: the exchange costs one NVLink round trip inside the update kernel.  A slot
-// of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's data of
-// call c + 1, which was sent after this rank finished reading call c: two parities are enough.
+// Every rank owns an exchange area [2 call parities][nranks][T][12] of 8-byte words; peer[j] is rank j's area mapped
+// into this process (CUDA IPC).  CTA t merges this rank's CTA partials for step t and sends the 48-byte result to every
+// rank (its own included: one code path) in the low-latency style of NCCL's LL protocol: each 8-byte word carries 4
+// bytes of payload and the 32-bit call id, and 8-byte stores are single NVLink transactions, so a word whose upper half
+// shows the current call id IS its payload - no fence, no separate flag, one NVLink write latency.  The CTA then spins
+// on the 12 x nranks words of its own area, and thread 0 folds the nranks results in rank order (identical on every
+// rank, so the plan stays replicated without a broadcast) and applies the update.  No NCCL call, no extra launch.
+// A slot of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's
+// data of call c + 1, which was sent after this rank finished reading call c: two parities are enough.
 constexpr int kMppiMaxRanks = 64;
+constexpr int kMppiXchgWords = 12;                // 6 doubles = 12 payload halves
 
 struct MppiXchgArgs
 {
-  double *peer_data[kMppiMaxRanks];               // rank j's data area  [2][nranks][T][6]
-  unsigned long long *peer_flag[kMppiMaxRanks];   // rank j's flag area  [2][nranks][T]
-  int rank, nranks;
-  unsigned long long call_id;                     // 1-based, strictly increasing
+  unsigned long long *peer[kMppiMaxRanks];        // rank j's area [2][nranks][T][12]
+  int rank, nranks, parity;                       // parity = call number & 1
+  uint32_t call_id;                               // call number folded into 1 .. 2^32 - 1: never 0 (the areas start zeroed)
 };
 
 __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kernel(const MppiUpdateArgs a, const __grid_constant__ MppiXchgArgs x)
 {
-  __shared__ double mine[6];
-  __shared__ double all[kMppiMaxRanks][6];
-  const int t = blockIdx.x, T = a.T, j = threadIdx.x;
-  const int par = (int)(x.call_id & 1ull);
+  __shared__ uint32_t mine[kMppiXchgWords];
+  __shared__ uint32_t all[kMppiMaxRanks][kMppiXchgWords];
+  const int t = blockIdx.x, T = a.T;
+  const int par = x.parity;
   asm volatile("griddepcontrol.wait;" ::: "memory");                 // programmatic dependent launch, as in mppi_update_kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
   mppi_block_merge(a.partials, a.n_partials, T, t, a.inv_lambda, m, S, A, B, DL, DR);
-  if (j == 0) { mine[0] = m; mine[1] = S; mine[2] = A; mine[3] = B; mine[4] = DL; mine[5] = DR; }
-  __syncthreads();
-  for (int r = j; r < x.nranks; r += kMppiUpdateThreads) {
-    // push to rank r (including this rank's own area: one code path)
-    const size_t slot = ((size_t)par * x.nranks + x.rank) * T + t;
-    double2 *dst = reinterpret_cast<double2 *>(x.peer_data[r] + slot * 6);
-    dst[0] = make_double2(mine[0], mine[1]);
-    dst[1] = make_double2(mine[2], mine[3]);
-    dst[2] = make_double2(mine[4], mine[5]);
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(x.peer_flag[r] + slot), "l"(x.call_id) : "memory");
-  }
-  for (int r = j; r < x.nranks; r += kMppiUpdateThreads) {
-    // pull rank r's result out of this rank's own area
-    const size_t slot = ((size_t)par * x.nranks + r) * T + t;
-    const unsigned long long *flag = x.peer_flag[x.rank] + slot;
-    unsigned long long seen;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-    } while (seen != x.call_id);
-    const double *src = x.peer_data[x.rank] + slot * 6;
+  if (threadIdx.x == 0) {
+    const double v[6] = {m, S, A, B, DL, DR};
 #pragma unroll
-    for (int i = 0; i < 6; i++) all[r][i] = __ldcv(src + i);
+    for (int i = 0; i < 6; i++) {
+      mine[2 * i] = (uint32_t)__double2loint(v[i]);
+      mine[2 * i + 1] = (uint32_t)__double2hiint(v[i]);
+    }
   }
   __syncthreads();
-  if (j != 0) return;
+  const int n_words = x.nranks * kMppiXchgWords;
+  for (int i = threadIdx.x; i < n_words; i += kMppiUpdateThreads) {
+    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
+    // word w of this rank's slot in rank r's area
+    unsigned long long *dst = x.peer[r] + (((size_t)par * x.nranks + x.rank) * T + t) * kMppiXchgWords + w;
+    const unsigned long long packed = ((unsigned long long)x.call_id << 32) | mine[w];
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(packed) : "memory");
+  }
+  for (int i = threadIdx.x; i < n_words; i += kMppiUpdateThreads) {
+    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
+    const unsigned long long *src = x.peer[x.rank] + (((size_t)par * x.nranks + r) * T + t) * kMppiXchgWords + w;
+    unsigned long long got;
+    do {
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+    } while ((uint32_t)(got >> 32) != x.call_id);
+    all[r][w] = (uint32_t)got;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  auto val = [&](int r, int i) { return __hiloint2double((int)all[r][2 * i + 1], (int)all[r][2 * i]); };
   m = inf;
-  for (int r = 0; r < x.nranks; r++) m = fmin(m, all[r][0]);
+  for (int r = 0; r < x.nranks; r++) m = fmin(m, val(r, 0));
   S = A = B = DL = DR = 0.0;
   for (int r = 0; r < x.nranks; r++) {
-    if (all[r][0] != inf) {
-      const double f = (all[r][0] == m) ? 1.0 : mppi_exp_neg((m - all[r][0]) * a.inv_lambda);
-      S = fma(all[r][1], f, S); A = fma(all[r][2], f, A); B = fma(all[r][3], f, B);
+    const double mr = val(r, 0);
+    if (mr != inf) {
+      const double f = (mr == m) ? 1.0 : mppi_exp_neg((m - mr) * a.inv_lambda);
+      S = fma(val(r, 1), f, S); A = fma(val(r, 2), f, A); B = fma(val(r, 3), f, B);
     }
-    DL += all[r][4]; DR += all[r][5];
+    DL += val(r, 4); DR += val(r, 5);
   }
   mppi_apply_update(a, t, m, S, A, B, DL, DR);
 }
