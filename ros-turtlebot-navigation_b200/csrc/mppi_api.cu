@@ -38,7 +38,6 @@ struct b2n_mppi
   double *d_partials = nullptr;          // [grid][T][6]
   double *d_merged = nullptr;            // [T][6]
   double *d_gathered = nullptr;          // [nranks][T][6]
-  double *d_out = nullptr;               // [2]
   double *d_stepstats = nullptr;         // [T][2]
   double *h_out = nullptr;               // pinned, mapped [2]: the update kernel writes the controls here
   double *d_out_host = nullptr;          // device view of h_out
@@ -367,7 +366,6 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_TRY(cudaMalloc(&h->d_states, KT * 3 * sizeof(float)));
   B2N_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * T * 6 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_merged, (size_t)T * 6 * sizeof(double)));
-  B2N_TRY(cudaMalloc(&h->d_out, 2 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_stepstats, (size_t)T * 2 * sizeof(double)));
   B2N_TRY(cudaHostAlloc(&h->h_out, 4 * sizeof(double), cudaHostAllocMapped));
   std::memset(h->h_out, 0, 4 * sizeof(double));
@@ -390,7 +388,7 @@ void b2n_mppi_destroy(b2n_mppi *h)
   cudaFree(h->xchg);
   for (auto e : h->ev) cudaEventDestroy(e);
   cudaFree(h->d_u[0]); cudaFree(h->d_u[1]); cudaFree(h->d_states); cudaFree(h->d_partials);
-  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_out); cudaFree(h->d_stepstats);
+  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_stepstats);
   cudaFree(h->d_ext); cudaFree(h->d_J); cudaFree(h->d_du); cudaFree(h->d_w); cudaFree(h->d_obs);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
