@@ -1061,16 +1061,21 @@ struct PfResample
 __global__ void __launch_bounds__(32) rbpf_normalize_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
 {
   const int lane = threadIdx.x;
+  // sequential sums in index order (:442-465); the next 32 weights are already in flight while a chunk is consumed
   double sum = 0.0;
+  double nxt = lane < n_total ? r.w[lane] : 0.0;
   for (int base = 0; base < n_total; base += 32) {
-    const double v = base + lane < n_total ? r.w[base + lane] : 0.0;
+    const double v = nxt;
+    nxt = base + 32 + lane < n_total ? r.w[base + 32 + lane] : 0.0;
     const int cnt = min(32, n_total - base);
     for (int i = 0; i < cnt; i++) sum += __shfl_sync(kFullMask, v, i);
   }
   double sq = 0.0;
+  nxt = lane < n_total ? r.w[lane] : 0.0;
   for (int base = 0; base < n_total; base += 32) {
     double v = 0.0;
-    if (base + lane < n_total) { v = r.w[base + lane] / sum; r.w[base + lane] = v; }
+    if (base + lane < n_total) { v = nxt / sum; r.w[base + lane] = v; }
+    nxt = base + 32 + lane < n_total ? r.w[base + 32 + lane] : 0.0;
     const int cnt = min(32, n_total - base);
     for (int i = 0; i < cnt; i++) { const double wi = __shfl_sync(kFullMask, v, i); sq += wi * wi; }   // std::pow(w, 2)
   }
@@ -1082,23 +1087,37 @@ __global__ void __launch_bounds__(32) rbpf_normalize_kernel(PfResample r, int n_
     for (int m = lane; m < n_total; m += 32) r.ancestors[m] = m;
     return;
   }
-  if (lane == 0) {
-    double z;
-    if (q.ext) z = q.ext[(size_t)q.ext_per];                               // caller passes a pointer to the last variate
-    else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
-    const double rr = z / (double)n_total;                                 // :475-476
-    double cacc = r.w[0];
-    int i = 0;
-    const double step = 1.0 / (n_total - 1);
-    for (int m = 0; m < n_total; m++) {
-      const double U = rr + (double)(m * step);                            // :485
-      while (U > cacc) {
-        i++;
-        if (i > n_total - 1) { i = n_total - 1; break; }
-        cacc += r.w[i];
-      }
-      r.ancestors[m] = i;
+  // the low-variance walk (:468-500), streamed: the weights come 32 at a time through one coalesced load and are handed
+  // out by shuffle, every lane runs the same sequential chain (cumulative sum and comparisons in the reference's
+  // order), lane 0 records the ancestors.  Equivalent to the reference's nested loops: sample m takes the first i with
+  // U_m <= w_0 + ... + w_i, clamped to N - 1 when the weights run out.
+  double z;
+  if (q.ext) z = q.ext[(size_t)q.ext_per];                                 // caller passes a pointer to the last variate
+  else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
+  const double rr = z / (double)n_total;                                   // :475-476
+  const double step = 1.0 / (n_total - 1);
+  double chunk = lane < n_total ? r.w[lane] : 0.0;
+  double ahead = 32 + lane < n_total ? r.w[32 + lane] : 0.0;
+  double cacc = __shfl_sync(kFullMask, chunk, 0);
+  int i = 0, m = 0;
+  double U = rr + (double)(m * step);                                      // :485
+  for (;;) {
+    while (m < n_total && !(U > cacc)) {
+      if (lane == 0) r.ancestors[m] = i;
+      m++;
+      U = rr + (double)(m * step);
     }
+    if (m >= n_total) break;
+    i++;
+    if (i > n_total - 1) {                                                 // weights exhausted: the rest clamps to N - 1
+      for (int k = m + lane; k < n_total; k += 32) r.ancestors[k] = n_total - 1;
+      break;
+    }
+    if ((i & 31) == 0) {
+      chunk = ahead;
+      ahead = i + 32 + lane < n_total ? r.w[i + 32 + lane] : 0.0;
+    }
+    cacc += __shfl_sync(kFullMask, chunk, i & 31);
   }
 }
 
