@@ -14,6 +14,7 @@ import _oracle as orc  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 scans = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 hcap = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+icp = int(sys.argv[4]) if len(sys.argv) > 4 else 0     # 1: improved-proposal branch from the second scan on (Ticp = odometry increment)
 pkg = _pkg.load()
 poses, twists = orc.circle_path(scans)
 rng = np.random.default_rng(4)
@@ -24,6 +25,9 @@ f.seed(1)
 f.setKernelTiming(True)
 for i in range(scans):
     scan = orc.room_scan(poses[i + 1], rng=rng)
+    if icp and i > 0:
+        w, d = twists[i][0], twists[i][1]
+        f.scan_matcher.setResult(True, (w, d * np.cos(w / 2), d * np.sin(w / 2)))
     t0 = time.perf_counter()
     f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
     wall = (time.perf_counter() - t0) * 1e3
