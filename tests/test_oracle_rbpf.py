@@ -178,6 +178,40 @@ def test_oracle_matches_live_reference_on_the_200x200_map(icp):
 
 
 @needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_matches_live_reference_on_random_scans(seed):
+    """Independent random ranges per beam (gated-out beams included) from random poses: rays in every direction class,
+    scattered obstacle cells, distance fields grown from scattered seeds.  Same inputs as the GPU test of the same name."""
+    rng = np.random.default_rng(1000 + seed)
+    N, scans = 6, 5
+    start = (float(rng.uniform(-3, 3)), float(rng.uniform(-0.8, 0.8)), float(rng.uniform(-0.8, 0.8)))
+    kw = dict(num_particles=N, init_pose=start, motion_noise=(4e-3, 2e-3, 2e-3))
+    o = orc.OraclePf(**kw)
+    r = orc.RefPf(**kw)
+    o.noise_mt19937(seed)
+    r.seed(seed)
+    prev = start
+    for i in range(scans):
+        cur = (prev[0] + float(rng.uniform(-0.3, 0.3)), prev[1] + float(rng.uniform(-0.05, 0.05)), prev[2] + float(rng.uniform(-0.05, 0.05)))
+        twist = (cur[0] - prev[0], float(np.hypot(cur[1] - prev[1], cur[2] - prev[2])), 0.0)
+        scan = rng.uniform(0.05, 3.45, 360).astype(np.float32)
+        scan[rng.integers(0, 360, 25)] = np.float32(4.5)
+        scan[rng.integers(0, 360, 10)] = np.float32(0.1)
+        assert o.slam(scan, twist, cur, prev) == 0
+        assert r.slam(scan, twist, cur, prev) == 0
+        prev = cur
+        so, sr = o.state(), r.state()
+        for k in so:
+            assert np.array_equal(so[k], sr[k]), (i, k)
+        for p in range(N):
+            go, gr = o.grid(p), r.grid(p)
+            for k in go:
+                assert np.array_equal(go[k], gr[k]), (i, p, k)
+            assert np.array_equal(o.occ_order(p), r.occ_order(p))
+        assert np.array_equal(o.new_map(), r.new_map())
+
+
+@needs_ref
 def test_bresenham_all_octants_match_reference():
     """Every direction class of GridMapper::freeGridIndex (grid_mapper.cpp:549-704), including the reversed-order
     and start-cell quirks, on random end points around random poses."""
