@@ -274,3 +274,43 @@ def test_error_behaviour(gpu_pkg):
         gpu.costToGo()                                   # capture was not switched on
     with pytest.raises(B2NError):
         gpu.setNoise(np.zeros((8, 63, 2)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_problems_match_oracle(gpu_pkg, seed):
+    """Random cost weights, temperatures, robot geometry, horizons (odd step counts: partially filled lanes), rollout counts,
+    waypoints and poses; capture taps on (generic kernel variant) for the first calls and off (FAST variant where the
+    horizon allows it) for the rest."""
+    rng = np.random.default_rng(500 + seed)
+    T = int(rng.choice([3, 17, 25, 37, 64, 90, 128, 200]))
+    dt = float(rng.choice([0.01, 0.02, 0.05]))
+    hor = (T + 0.5) * dt
+    K = int(rng.integers(2, 700))
+    prm = dict(wheel_radius=float(rng.uniform(0.02, 0.06)), wheel_base=float(rng.uniform(0.1, 0.3)),
+               Q=tuple(10.0 ** rng.uniform(-1, 4, 3)), R=tuple(10.0 ** rng.uniform(-2, 0, 2)), P1=tuple(10.0 ** rng.uniform(0, 3, 3)),
+               lambda_=float(10.0 ** rng.uniform(-2, 1)), max_wheel_vel=float(rng.uniform(2.0, 8.0)),
+               ul_var=float(rng.uniform(0.1, 1.5)), ur_var=float(rng.uniform(0.1, 1.5)))
+    o = orc.OracleMppi(hor, dt, K, **prm)
+    gpu = make_gpu(gpu_pkg, hor, dt, K, prm)
+    assert gpu.steps == o.T == T
+    gpu.seed(seed)
+    o.noise_philox(seed)
+    u0 = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)))
+    gpu.setInitialControls(*u0)
+    o.setInitialControls(*u0)
+    wp = (float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2)), float(rng.uniform(-3, 3)))
+    gpu.setWaypoint(gpu_pkg.Pose(theta=wp[2], x=wp[0], y=wp[1]))
+    o.setWaypoint(*wp)
+    pose = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), float(rng.uniform(-3, 3)))
+    for c in range(6):
+        gpu.setCapture(c < 2)
+        v = gpu.newControls(gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        co = o.newControls(*pose)
+        if c < 2:
+            check_call(gpu, o, (v.ul, v.ur), co)
+        else:
+            assert rel_err([v.ul, v.ur], co, 1e-3) < RTOL
+            assert rel_err(gpu.plan(), o.get()["plan"], 1e-3) < RTOL
+            s, so = gpu.states(), o.get()["states"]
+            assert np.max(np.abs(s - so) / np.maximum(np.abs(so), 1e-2)) < RTOL
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
