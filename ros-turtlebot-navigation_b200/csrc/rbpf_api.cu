@@ -216,7 +216,7 @@ int configure_df(b2n_pf *h)
     const int W = (per_sm + ng - 1) / ng;
     const int cols_per_warp = ng * cols_needed;
     int hcap = 0;
-    const size_t stage_bytes = (size_t)W * ng * 64 * 4;
+    const size_t stage_bytes = (size_t)W * ng * (64 * 4 + 4 * 8);
     if (((W + 3) / 4) * cols_per_warp <= 512 && budget > stage_bytes + 1024) {
       hcap = (int)((budget - stage_bytes) / ((size_t)W * ng) / 8) - 2;
       hcap = std::min(hcap & ~1, 16384);

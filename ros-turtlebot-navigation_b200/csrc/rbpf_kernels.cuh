@@ -899,7 +899,8 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
 
 __host__ __device__ inline size_t pf_dfg_smem_bytes(int hcap, int warps, int ng)
 {
-  return (size_t)warps * ng * (size_t)(hcap + 2) * 8 + (size_t)warps * ng * 64 * 4;
+  // heaps, then per warp the staged bitmap windows [ng][2][32] words and the candidate entries [ng][4] x 8 bytes
+  return (size_t)warps * ng * (size_t)(hcap + 2) * 8 + (size_t)warps * ng * (64 * 4 + 4 * 8);
 }
 
 template <int GL>
@@ -911,7 +912,6 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
   __shared__ uint32_t tmem_base_slot;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane / GL, sl = lane % GL;
-  const unsigned gmask = ((GL == 32) ? 0xFFFFFFFFu : ((1u << GL) - 1u)) << (q * GL);
   const int slots = d.warps * NG, slot = warp * NG + q;
   const int words = (c.G + 31) / 32, cols = (words + 31) / 32;
   const int CG = cols + 1;                                               // TMEM columns per particle (one spare for the x2 loads)
@@ -930,8 +930,11 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
   H.sb = smem_u32(smem) + (uint32_t)slot * (uint32_t)(d.hcap + 2) * 8u;
   H.g = reinterpret_cast<uint2 *>(d.spill) + ((size_t)blockIdx.x * slots + slot) * d.gcap;
   H.hcap = d.hcap; H.gcap = d.gcap; H.overflow = false; H.len = 0;
-  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + (size_t)slots * (d.hcap + 2) * 8) + (size_t)warp * NG * 64;   // [NG][2][32]
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem + (size_t)slots * (d.hcap + 2) * 8) + (size_t)warp * NG * (64 + 8);   // [NG][2][32]
   uint32_t *my_stage = stage + q * 64;
+  // candidate entries of the group's four testers, handed to the whole group through shared memory (a shuffle with a
+  // per-group mask inside the divergent push loop costs a dozen instructions of mask checking)
+  const uint32_t cand = smem_u32(stage + NG * 64) + (uint32_t)q * 32u;
   unsigned long long iters = 0;
   int heap_max = 0;
   // lanes 0..3 of a group test (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
@@ -1010,8 +1013,8 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
       if (valid) {
         d2n[idx0] = (uint32_t)d2;
         atomicOr(wp, 1u << (idx & 31));
+        sts64(cand + 8u * (uint32_t)sl, make_uint2(top.x + dEntry, (uint32_t)d2));
       }
-      const uint2 entry = make_uint2(top.x + dEntry, (uint32_t)d2);
       const unsigned vmask = __ballot_sync(kFullMask, valid);
       if (vmask) {
         __syncwarp();
@@ -1025,9 +1028,9 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
       if (m) {
         const bool shared_ok = H.len + 4 <= H.hcap;
         do {
-          const int from = q * GL + __ffs(m) - 1;
+          const int from = __ffs(m) - 1;
           m &= m - 1;
-          const uint2 e = make_uint2(__shfl_sync(gmask, entry.x, from), __shfl_sync(gmask, entry.y, from));
+          const uint2 e = lds64(cand + 8u * (uint32_t)from);
           if (shared_ok) H.push_shared(e);
           else H.push_any(e);
         } while (m);
