@@ -187,7 +187,20 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
             mine = torch.frombuffer(bytearray(f.p2pExport()), dtype=torch.uint8).cuda()
             hs = [torch.zeros(640, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(hs, mine)
-            f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+            ok = torch.ones(1, dtype=torch.int32, device="cuda")
+            try:
+                f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+            except pkg.B2NError:
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:                 # some rank cannot map its peers: everyone migrates with ncclSend/ncclRecv
+                exchange = "nccl"
+                f.close()
+                f = pkg.bmapping.make_filter(q, particle_offset=rank * RBPF_N, particles_total=world * RBPF_N, device=local)
+                if rank == 0:
+                    uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(uid, 0)
+                f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
     else:
         f = pkg.bmapping.make_filter(q, device=local)
     f.seed(1)
@@ -319,6 +332,8 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d" % (args.gpus, args.gpus))
     if lib.b2n_device_count() < 1:
         raise SystemExit("bench.py: libb2nav sees no CUDA device (there is no CPU path)")
+    if torch.cuda.device_count() <= local:          # launcher restricted each rank to its own GPU
+        local = 0
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
@@ -336,11 +351,27 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         mppi.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
         if args.exchange == "p2p":
-            # exchange inside the update kernel over NVLink peer memory: gather every rank's CUDA IPC handle
+            # exchange inside the update kernel over NVLink peer memory: gather every rank's CUDA IPC handle; if any
+            # rank cannot map its peers (no peer access, GPUs hidden from each other) every rank stays on ncclAllGather
             mine = torch.frombuffer(bytearray(mppi.p2pExport(world)), dtype=torch.uint8).cuda()
             hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(hs, mine)
-            mppi.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+            ok = torch.ones(1, dtype=torch.int32, device="cuda")
+            try:
+                mppi.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+            except pkg.B2NError:
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                args.exchange = "nccl"
+                mppi.close()
+                mppi = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
+                                prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], HORIZON, DT, K_ROLLOUTS,
+                                rollout_offset=rank * K_ROLLOUTS, rollouts_total=world * K_ROLLOUTS, device=local)
+                if rank == 0:
+                    uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(uid, 0)
+                mppi.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
     # the handle launches on THIS stream and the timing events are recorded on it (torch's current stream is the
     # legacy default stream, handle 0, which b2n_mppi_set_stream reads as "use your own": events there would bracket
     # nothing but the host's enqueue loop)
@@ -422,7 +453,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "dtype": "f64", "data": "synthetic", "config": dict(workload_config(world), exchange=(args.exchange if world > 1 else "none")), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24,
                     "d2h_bytes_per_step": 16,
                     "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the update kernel into mapped pinned memory"},
