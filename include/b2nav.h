@@ -224,6 +224,9 @@ int b2n_pf_set_kernel_timing(b2n_pf *h, int on);
 int b2n_pf_kernel_times(b2n_pf *h, double ms[3]);
 /* brushfire iterations summed over all particles and calls, largest heap seen */
 int b2n_pf_distance_field_stats(b2n_pf *h, uint64_t *iterations, uint64_t *heap_max);
+/* particle-scans (summed over calls) whose distance field was NOT regrown because their occupied set had not changed
+ * since it was last grown - the field is a deterministic function of that set's iteration order */
+int b2n_pf_distance_field_skipped(b2n_pf *h, uint64_t *particles);
 /* heap entries kept in shared memory per particle in flight (the rest spills to global memory); default 2048 */
 int b2n_pf_set_heap_capacity(b2n_pf *h, int entries);
 /* what create() derives on the HOST from the constructor arguments, without needing a device (CPU tests):

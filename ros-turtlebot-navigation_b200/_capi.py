@@ -106,6 +106,7 @@ PROTOTYPES = {
     "b2n_pf_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "b2n_pf_kernel_times": (C.c_int, [_vp, _P(D)]),
     "b2n_pf_distance_field_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
+    "b2n_pf_distance_field_skipped": (C.c_int, [_vp, _P(C.c_uint64)]),
     "b2n_pf_set_heap_capacity": (C.c_int, [_vp, C.c_int]),
     "b2n_pf_host_tables": (C.c_int, [_P(PfParams), _P(D), _vp, _sz, _vp, _sz, _P(C.c_int)]),
     "b2n_pf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

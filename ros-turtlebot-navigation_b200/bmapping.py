@@ -195,6 +195,11 @@ class ParticleFilter:
         _capi.check(self._lib.b2n_pf_distance_field_stats(self._h, C.byref(it), C.byref(hm)))
         return it.value, hm.value
 
+    def distanceFieldSkipped(self):
+        n = C.c_uint64()
+        _capi.check(self._lib.b2n_pf_distance_field_skipped(self._h, C.byref(n)))
+        return n.value
+
     def setHeapCapacity(self, entries):
         _capi.check(self._lib.b2n_pf_set_heap_capacity(self._h, int(entries)))
 

@@ -45,6 +45,7 @@ struct b2n_pf
   int df_gl_active = 32;
   int df_gl = 16;                     // lanes per particle in the distance-field kernel: 32 (one particle per warp), 16 or 8
   bool df_tmem = true, df_tmem_active = true;
+  bool df_skip_clean = true;          // do not regrow a distance field whose occupied set did not change (B2N_PF_DF_ALWAYS=1: always)
   size_t df_smem = 0, spill_entries = 0;
   size_t smem_optin = 0;
   double *d_best = nullptr, *h_best = nullptr;   // pose[3], weight
@@ -119,6 +120,7 @@ __global__ void pf_init_kernel(const __grid_constant__ PfConst c, PfPlanes pl, d
     q.pose[0] = q.prev_pose[0] = th; q.pose[1] = q.prev_pose[1] = x; q.pose[2] = q.prev_pose[2] = y;
     q.weight = weight;
     q.n_occ = 0; q.bucket_count = 1; q.next_resize = 0; q.chain = -1;   // an empty std::unordered_set
+    q.occ_dirty = 0;
     pl.meta[i] = q;
   }
 }
@@ -510,8 +512,8 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
   B2N_TRY(cudaMallocHost(&h->h_best, 4 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_map, (size_t)G));
   B2N_TRY(cudaMalloc(&h->d_lik, sizeof(double) * h->N));
-  B2N_TRY(cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)));
-  B2N_TRY(cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(unsigned long long), h->stream));
+  B2N_TRY(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
+  B2N_TRY(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
 
   // distance-field launch shape
   h->smem_optin = prop.sharedMemPerBlockOptin;
@@ -521,6 +523,7 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
   B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_groups_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
   B2N_TRY(cudaFuncSetAttribute(rbpf_distance_field_groups_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
   if (const char *env = std::getenv("B2N_PF_DF_SMEM_MARKS")) h->df_tmem = env[0] != '1';
+  if (const char *env = std::getenv("B2N_PF_DF_ALWAYS")) h->df_skip_clean = env[0] != '1';
   if (const char *env = std::getenv("B2N_PF_DF_LANES")) { const int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) h->df_gl = v; }
   if (configure_df(h) != B2N_OK) { b2n_pf_destroy(h); return B2N_ERR_CUDA; }
   if (pf_smem_bytes(h->max_beams, c.pz_stage, kPfWarpsPerCta) > prop.sharedMemPerBlockOptin) {
@@ -623,7 +626,7 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   // euclideanSignedDistanceField at the end of every integrateScan (grid_mapper.cpp:181)
   {
     PfDfArgs d;
-    d.hcap = h->df_hcap; d.gcap = h->df_gcap; d.warps = h->df_warps; d.cols_per_warp = h->df_cols;
+    d.hcap = h->df_hcap; d.gcap = h->df_gcap; d.warps = h->df_warps; d.cols_per_warp = h->df_cols; d.skip_clean = h->df_skip_clean ? 1 : 0;
     d.spill = h->d_spill; d.stats = h->d_stats; d.status = h->d_status;
     if (h->df_gl_active == 8) rbpf_distance_field_groups_kernel<8><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
     else if (h->df_gl_active == 16) rbpf_distance_field_groups_kernel<16><<<h->df_grid, h->df_warps * 32, h->df_smem, h->stream>>>(c, pl, d);
@@ -964,6 +967,17 @@ int b2n_pf_distance_field_stats(b2n_pf *h, uint64_t *iterations, uint64_t *heap_
   B2N_CUDA(cudaMemcpy(s, h->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
   if (iterations) *iterations = s[0];
   if (heap_max) *heap_max = s[1];
+  return B2N_OK;
+}
+
+int b2n_pf_distance_field_skipped(b2n_pf *h, uint64_t *particles)
+{
+  B2N_REQUIRE(h && particles, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = set_device(h)) return rc;
+  B2N_CUDA(cudaStreamSynchronize(h->stream));
+  unsigned long long s = 0;
+  B2N_CUDA(cudaMemcpy(&s, h->d_stats + 2, sizeof(s), cudaMemcpyDeviceToHost));
+  *particles = s;
   return B2N_OK;
 }
 

@@ -46,6 +46,7 @@ struct PfParticle
   double weight;
   uint32_t n_occ, bucket_count, next_resize;
   int32_t chain;
+  uint32_t occ_dirty;             // the occupied set changed since the distance field was last grown from it
 };
 
 struct PfPlanes
@@ -134,6 +135,7 @@ struct OccSetDev
   uint16_t *nxt, *bkt;
   uint32_t G, bucket_count, count, next_resize;
   int chain;
+  uint32_t dirty;                 // any insert / erase (a rehash only happens inside an insert)
 };
 
 // _Hashtable::_M_rehash_aux (unique keys).  Executed by every lane with identical data (same addresses, same
@@ -328,6 +330,7 @@ __device__ __forceinline__ void pf_integrate_rays(const PfConst &c, const uint32
         const int src = __ffs(m) - 1;
         const uint32_t key = __shfl_sync(kFullMask, cell, src);
         occ_erase(occ, key, lane);
+        occ.dirty = 1u;
         m &= m - 1;
       }
     }
@@ -338,7 +341,7 @@ __device__ __forceinline__ void pf_integrate_rays(const PfConst &c, const uint32
     const double ln = lo + c.d_occ;
     __syncwarp();
     if (lane == 0) L[cell] = ln;
-    if (!(lo >= c.t_occ) && (ln >= c.t_occ)) occ_insert(occ, cell, lane);
+    if (!(lo >= c.t_occ) && (ln >= c.t_occ)) { occ_insert(occ, cell, lane); occ.dirty = 1u; }
     __syncwarp();
   }
 }
@@ -426,13 +429,14 @@ __global__ void __launch_bounds__(kPfWarpsPerCta * 32) rbpf_update_kernel(const 
   OccSetDev occ;
   occ.nxt = pl.nxt + (size_t)p * c.nxt_stride; occ.bkt = pl.bkt + (size_t)p * c.bkt_stride;
   occ.G = (uint32_t)c.G; occ.bucket_count = me->bucket_count; occ.count = n_occ; occ.next_resize = me->next_resize;
-  occ.chain = me->chain;
+  occ.chain = me->chain; occ.dirty = me->occ_dirty;
   pf_integrate_rays(c, w_ep, n, i0, j0, pl.log_odds + (size_t)p * c.gstride, occ, lane);
 
   if (lane == 0) {
     me->pose[0] = th; me->pose[1] = x; me->pose[2] = y;
     me->weight = me->weight * lik;                         // particle_filter.cpp:175
     me->n_occ = occ.count; me->bucket_count = occ.bucket_count; me->next_resize = occ.next_resize; me->chain = occ.chain;
+    me->occ_dirty = occ.dirty;
   }
 }
 
@@ -571,12 +575,13 @@ __global__ void __launch_bounds__(kPfWarpsPerCta * 32) rbpf_proposal_kernel(cons
   OccSetDev occ;
   occ.nxt = pl.nxt + (size_t)p * c.nxt_stride; occ.bkt = pl.bkt + (size_t)p * c.bkt_stride;
   occ.G = (uint32_t)c.G; occ.bucket_count = me->bucket_count; occ.count = n_occ; occ.next_resize = me->next_resize;
-  occ.chain = me->chain;
+  occ.chain = me->chain; occ.dirty = me->occ_dirty;
   pf_integrate_rays(c, w_ep, n, i0, j0, pl.log_odds + (size_t)p * c.gstride, occ, lane);
   if (lane == 0) {
     for (int i = 0; i < 3; i++) { me->prev_pose[i] = pose[i]; me->pose[i] = np[i]; }
     me->weight = me->weight * eta;                                      // :231
     me->n_occ = occ.count; me->bucket_count = occ.bucket_count; me->next_resize = occ.next_resize; me->chain = occ.chain;
+    me->occ_dirty = occ.dirty;
   }
 }
 
@@ -741,7 +746,7 @@ __host__ __device__ inline size_t pf_df_smem_bytes(int G, int hcap, int warps, b
 
 struct PfDfArgs
 {
-  int hcap, gcap, warps, cols_per_warp;
+  int hcap, gcap, warps, cols_per_warp, skip_clean;
   unsigned long long *spill;   // [gridDim.x * warps][gcap]
   unsigned long long *stats;
   int *status;
@@ -775,7 +780,7 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_kerne
   H.g = reinterpret_cast<uint2 *>(d.spill) + ((size_t)blockIdx.x * d.warps + warp) * d.gcap;
   H.hcap = d.hcap; H.gcap = d.gcap; H.overflow = false;
   uint32_t *marked = TMEM_MARKS ? nullptr : reinterpret_cast<uint32_t *>(smem + (size_t)d.warps * (d.hcap + 2) * 8) + (size_t)warp * words;
-  unsigned long long iters = 0;
+  unsigned long long iters = 0, skipped = 0;
   int heap_max = 0;
   // lanes 0..3 test (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
   const int dI = lane == 0 ? -1 : lane == 2 ? 1 : 0, dJ = lane == 1 ? -1 : lane == 3 ? 1 : 0;
@@ -785,8 +790,13 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_kerne
   const int R2 = R * R;
 
   for (int p = blockIdx.x * d.warps + warp; p < c.N; p += gridDim.x * d.warps) {
-    const PfParticle *me = pl.meta + p;
+    PfParticle *me = pl.meta + p;
     if (me->n_occ == 0) continue;                                        // grid_mapper.cpp:335-338
+    // the field is a deterministic function of the occupied set's iteration order (cells nothing reaches keep their
+    // value): an untouched set would reproduce the field that is already there
+    if (d.skip_clean && me->occ_dirty == 0) { skipped++; continue; }
+    __syncwarp();
+    if (lane == 0) me->occ_dirty = 0;
     const uint16_t *nxt = pl.nxt + (size_t)p * c.nxt_stride;
     uint32_t *d2p = pl.d2 + (size_t)p * c.gstride;
     const int cols = (words + 31) / 32;
@@ -871,7 +881,7 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_kerne
     }
     iters += it;
   }
-  if (d.stats && lane == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); }
+  if (d.stats && lane == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); atomicAdd(&d.stats[2], skipped); }
   if (H.overflow && lane == 0) atomicOr(d.status, kDfStatusHeapOverflow);
   if (TMEM_MARKS) {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -935,7 +945,7 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
   // candidate entries of the group's four testers, handed to the whole group through shared memory (a shuffle with a
   // per-group mask inside the divergent push loop costs a dozen instructions of mask checking)
   const uint32_t cand = smem_u32(stage + NG * 64) + (uint32_t)q * 32u;
-  unsigned long long iters = 0;
+  unsigned long long iters = 0, skipped = 0;
   int heap_max = 0;
   // lanes 0..3 of a group test (i-1, j), (i, j-1), (i+1, j), (i, j+1)  (:401-427)
   const int dI = sl == 0 ? -1 : sl == 2 ? 1 : 0, dJ = sl == 1 ? -1 : sl == 3 ? 1 : 0;
@@ -946,7 +956,11 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
 
   for (int p0 = blockIdx.x * slots; p0 < c.N; p0 += gridDim.x * slots) {
     const int p = p0 + slot;
-    const bool act = p < c.N && pl.meta[min(p, c.N - 1)].n_occ != 0;     // grid_mapper.cpp:335-338
+    bool act = p < c.N && pl.meta[min(p, c.N - 1)].n_occ != 0;           // grid_mapper.cpp:335-338
+    // an untouched occupied set would reproduce the field that is already there (see the single-particle kernel)
+    if (act && d.skip_clean && pl.meta[p].occ_dirty == 0) { act = false; if (sl == 0) skipped++; }
+    __syncwarp();
+    if (act && sl == 0) pl.meta[p].occ_dirty = 0;
     const uint16_t *nxt = pl.nxt + (size_t)min(p, c.N - 1) * c.nxt_stride;
     uint32_t *d2p = pl.d2 + (size_t)min(p, c.N - 1) * c.gstride;
     uint32_t *d2n = d2p + dIdx;
@@ -1045,7 +1059,7 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
     }
     iters += it;
   }
-  if (d.stats && sl == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); }
+  if (d.stats && sl == 0) { atomicAdd(&d.stats[0], iters); atomicMax(&d.stats[1], (unsigned long long)heap_max); atomicAdd(&d.stats[2], skipped); }
   if (H.overflow && sl == 0) atomicOr(d.status, kDfStatusHeapOverflow);
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();

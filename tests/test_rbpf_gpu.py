@@ -304,3 +304,27 @@ def test_random_scans_exercise_every_ray_direction(gpu_pkg, seed):
         assert np.array_equal(f.resampleInfo()[2], o.resample_info()[2])
         assert rel(f.weights(), o.state()["weights"]) < 1e-9
         assert np.array_equal(f.newMap(), o.new_map())
+
+
+def test_unchanged_occupied_set_skips_the_distance_field_and_changes_nothing(gpu_pkg):
+    """A robot standing still with four isolated returns: after the first scan no cell enters or leaves the occupied set,
+    so the brushfire would reproduce the field that is already there - the kernel skips it; the oracle (which regrows it
+    every scan, like the reference) must still agree bit for bit.  (With a full room scan the set is touched every scan:
+    grazing rays erase and re-insert wall cells, which also reorders the set.)"""
+    N, scans = 5, 4
+    pose = (0.3, 0.4, -0.2)
+    kw = dict(num_particles=N, init_pose=pose, motion_noise=(0.0, 0.0, 0.0))
+    f = make_gpu(gpu_pkg, **kw)
+    o = orc.OraclePf(**kw)
+    f.seed(1)
+    o.noise_philox(1)
+    scan = np.full(360, 4.5, dtype=np.float32)          # everything out of range ...
+    scan[[10, 100, 190, 280]] = np.float32(2.0)         # ... except four well separated hits: no ray crosses another's end cell
+    for i in range(scans):
+        assert o.slam(scan, (0.0, 0.0, 0.0), pose, pose) == 0
+        slam_gpu(gpu_pkg, f, scan, (0.0, 0.0, 0.0), pose, pose)
+        for k in range(N):
+            assert_grid_equal(f.grid(k), o.grid(k))
+            assert np.array_equal(f.occOrder(k), o.occ_order(k))
+        assert rel(f.weights(), o.state()["weights"]) < 1e-9
+    assert f.distanceFieldSkipped() == (scans - 1) * N

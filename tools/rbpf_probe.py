@@ -35,4 +35,4 @@ for i in range(scans):
     neff, rs, _ = f.resampleInfo()
     print("scan %d: wall %.2f ms | update %.3f ms, distance field %.3f ms, normalise+resample %.3f ms | N_eff %d resampled %d | %.0f particle-updates/s"
           % (i, wall, ms[0], ms[1], ms[2], neff, rs, N / (wall * 1e-3)))
-print("distance-field stats (iterations, heap max):", f.distanceFieldStats())
+print("distance-field stats (iterations, heap max):", f.distanceFieldStats(), "particle-scans skipped (occupied set unchanged):", f.distanceFieldSkipped())
