@@ -102,7 +102,7 @@ cudaError_t configure_shape(b2n_mppi *h)
 
 // (7-warp CTAs, four per SM, divide K = 16384 into equal passes - measured no faster than 8-warp CTAs (22.2 vs 20.5 us):
 // the kernel is bound by the dependent instruction stream of a pass, not by the half-empty last pass; not instantiated)
-#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8)
+#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8) X(4, 16, 7)
 
 cudaError_t configure(b2n_mppi *h)
 {
@@ -195,13 +195,13 @@ MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
 }
 
 // the FAST variant needs: own noise, no taps, no obstacle term, a full last lane, TMA stores, and every half-step
-// heading increment inside the Taylor range of mppi_sincos_small: |h w / 2| <= c_w (|uL| + |uR|) / 2 with
+// heading increment inside the short Taylor range of mppi_sincos_small (1/16): |h w / 2| <= c_w (|uL| + |uR|) / 2 with
 // |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
 bool fast_variant(const b2n_mppi *h, const MppiArgs &a)
 {
   const double u_bound = 2.0 * h->plan_abs_max + 5.78 * (a.sigL + a.sigR);
   return !a.external_noise && !a.capture && !a.obs_on && a.tma_store && h->T == h->S * h->G &&
-         0.5 * std::fabs(a.c_w) * u_bound <= 0.125 && !h->force_generic;
+         0.5 * std::fabs(a.c_w) * u_bound <= 0.0625 && !h->force_generic;
 }
 
 // update kernel behind the rollout kernel with programmatic dependent launch: its CTAs may be scheduled while the

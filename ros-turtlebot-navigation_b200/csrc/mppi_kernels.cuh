@@ -91,12 +91,23 @@ __device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, double x
 // every term).
 __device__ __forceinline__ double mppi_exp_neg(double x) { return x > -708.0 ? exp(x) : 0.0; }
 
-// sin and cos of a small angle by Taylor series (|d| <= 1/8: truncation < 3e-16 relative); full range falls back
+// sin and cos of a small angle by Taylor series.  Generic: |d| <= 1/8 with terms to d^9 / d^10 (truncation < 3e-16
+// relative), full range falls back to sincos.  ALWAYS_SMALL (the host has proved |d| <= 1/16): terms to d^7 / d^6,
+// truncation 4e-17 / 6e-15 absolute.
 template <bool ALWAYS_SMALL>
 __device__ __forceinline__ void mppi_sincos_small(double d, double &sn, double &cs)
 {
-  if (!ALWAYS_SMALL && fabs(d) > 0.125) { sincos(d, &sn, &cs); return; }
   const double z = d * d;
+  if (ALWAYS_SMALL) {
+    double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);    // -1/7!, 1/5!
+    ps = fma(z, ps, -1.6666666666666666e-01);                               // -1/3!
+    sn = fma(d * z, ps, d);
+    double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);    // -1/6!, 1/4!
+    pc = fma(z, pc, -0.5);
+    cs = fma(z, pc, 1.0);
+    return;
+  }
+  if (fabs(d) > 0.125) { sincos(d, &sn, &cs); return; }
   double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
   ps = fma(z, ps, 8.3333333333333332e-03);                                // 1/5!
   ps = fma(z, ps, -1.6666666666666666e-01);                               // -1/3!
@@ -110,16 +121,18 @@ __device__ __forceinline__ void mppi_sincos_small(double d, double &sn, double &
 
 // dynamic shared memory: [warps][2][32*S*3] fp32 staging rows, then [S*6][threads] fp64 online-softmax accumulators
 // (kept out of the register file so that three CTAs fit an SM; reused as [warps][G*S][6] for the CTA merge)
+// (7-warp CTAs stage through ONE buffer so that four of them fit an SM)
+__host__ __device__ constexpr int mppi_stage_buffers(int NW) { return NW == 7 ? 1 : 2; }
 __host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW)
 {
-  return (size_t)NW * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * NW * 32 * sizeof(double);
+  return (size_t)NW * mppi_stage_buffers(NW) * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * NW * 32 * sizeof(double);
 }
 
 // FAST = the production configuration, decided on the host: own noise, no capture taps, no obstacle term, T == G * S
 // (no partially filled lanes), TMA row stores, and half-step heading increments provably inside the Taylor range.
 // NW = warps per CTA: 8, or 7 (four CTAs = 28 warps per SM) where that divides the job into equal passes.
 template <int S, int G, bool FAST, int NW>
-__global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+__global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 && NW != 7 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
 {
   constexpr int kMppiWarps = NW, kMppiThreads = NW * 32;     // shadow the defaults: every layout below follows the CTA shape
   static_assert(S % 2 == 0 && (G == 8 || G == 16 || G == 32), "a Philox call covers two steps; G lanes per rollout");
@@ -127,8 +140,9 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
   constexpr int TP = G * S;        // padded horizon
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *stage_base = reinterpret_cast<float *>(smem_raw);                                       // [warps][2][R*TP*3]
-  double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
-  double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * 2 * 32 * S * 3 * 4);             // [warps][TP][6] (epilogue)
+  constexpr int NBUF = mppi_stage_buffers(NW);
+  double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * NBUF * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
+  double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * NBUF * 32 * S * 3 * 4);             // (epilogue)
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
   const int t0 = g * S;            // first owned step
   const bool ext_noise = !FAST && a.external_noise, capture = !FAST && a.capture, obs_on = !FAST && a.obs_on;
   const bool tma_store = FAST || a.tma_store;
-  float *stage = stage_base + warp * 2 * (R * TP * 3);
+  float *stage = stage_base + warp * NBUF * (R * TP * 3);
 
   const double sin0 = a.sin0, cos0 = a.cos0;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
   // the plan it writes is read from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
   int buf = 0;
-  for (int base = gw * R; base < a.K; base += nw * R, buf ^= 1) {
+  for (int base = gw * R; base < a.K; base += nw * R, buf ^= (NBUF - 1)) {
     const int k = base + r;
     const bool live = k < a.K;
 
@@ -193,13 +207,18 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
         vh[s + j] = a.c_v * (uL + uR);                          // (h/6) v, v = (r/2)(uL + uR)   (mppi.hpp:45-46)
         dth[s + j] = a.c_w * (uR - uL);                         // h w, w = (r/L)(uR - uL): rk4.cpp:114 with k1 = k2 = k3 = k4
         mppi_sincos_small<FAST>(0.5 * dth[s + j], sd[s + j], cd[s + j]);
-        // full-step rotation, folded into the lane total
-        const double c2 = fma(cd[s + j], cd[s + j], -(sd[s + j] * sd[s + j])), s2 = 2.0 * (sd[s + j] * cd[s + j]);
-        const double nc = tc * c2 - ts * s2;
-        ts = fma(tc, s2, ts * c2);
+        // product of the lane's HALF-step rotations (squared once below: rotations commute)
+        const double nc = tc * cd[s + j] - ts * sd[s + j];
+        ts = fma(tc, sd[s + j], ts * cd[s + j]);
         tc = nc;
         tth += dth[s + j];
       }
+    }
+    {
+      // the lane's total rotation = (product of half steps)^2
+      const double nc = fma(tc, tc, -(ts * ts));
+      ts = 2.0 * (ts * tc);
+      tc = nc;
     }
 
     // ---- segmented inclusive scans over the rollout's G lanes: rotation product and heading sum ----------
@@ -231,8 +250,11 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
     for (int s = 0; s < S; s++) {
       const double mc = rc * cd[s] - rs * sd[s], ms = fma(rc, sd[s], rs * cd[s]);      // mid-step heading
       const double ec = mc * cd[s] - ms * sd[s], es = fma(mc, sd[s], ms * cd[s]);      // end-of-step heading
-      ax = fma(vh[s], fma(4.0, mc, rc + ec), ax);      // (h/6) v (k1 + 2 k2 + 2 k3 + k4), running sum inside the lane
-      ay = fma(vh[s], fma(4.0, ms, rs + es), ay);
+      // (h/6) v (k1 + 2 k2 + 2 k3 + k4): with the headings theta, theta + d, theta + 2 d the bracket is
+      // R (1 + 4 e^{id} + e^{2id}) = R e^{id} (4 + 2 cos d) - the mid-step heading scaled; running sum inside the lane
+      const double f = vh[s] * fma(2.0, cd[s], 4.0);
+      ax = fma(f, mc, ax);
+      ay = fma(f, ms, ay);
       px[s] = ax; py[s] = ay;
       th += dth[s];
       TH[s] = a.x0[2] + th;
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
     // ---- states after each step -> staging row; loss (mppi.cpp:99-105, mppi.hpp:87-105) -------------------
     float *row = stage + buf * (R * TP * 3) + r * (T * 3);
     if (tma_store) {
-      if (lane == 0) tma_store_wait_read<1>();   // the store issued two passes ago has drained this buffer
+      if (lane == 0) tma_store_wait_read<NBUF - 1>();   // the store that last used this buffer has drained it
       __syncwarp();
     }
     double J[S];
@@ -296,11 +318,16 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 ? 3 : 4))) mppi
         const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
         const double e = mppi_exp_neg(-fabs(d));
         const bool newmin = d > 0.0;
-        const double S0 = c[kMppiThreads], A0 = c[2 * kMppiThreads], B0 = c[3 * kMppiThreads];
-        c[kMppiThreads] = newmin ? fma(S0, e, 1.0) : S0 + e;
-        c[2 * kMppiThreads] = newmin ? fma(A0, e, duL[s]) : fma(e, duL[s], A0);
-        c[3 * kMppiThreads] = newmin ? fma(B0, e, duR[s]) : fma(e, duR[s], B0);
-        if (newmin) c[0] = Js;
+        // a rollout whose weight underflows against the running minimum leaves the three sums untouched - at the
+        // shipped temperature that is nearly every term, and the accumulators stay in shared memory unread
+        if (newmin || e != 0.0) {
+          const double S0 = c[kMppiThreads], A0 = c[2 * kMppiThreads], B0 = c[3 * kMppiThreads];
+          const double scale = newmin ? e : 1.0, add = newmin ? 1.0 : e;
+          c[kMppiThreads] = fma(S0, scale, add);
+          c[2 * kMppiThreads] = fma(A0, scale, add * duL[s]);
+          c[3 * kMppiThreads] = fma(B0, scale, add * duR[s]);
+          if (newmin) c[0] = Js;
+        }
         c[4 * kMppiThreads] += duL[s];
         c[5 * kMppiThreads] += duR[s];
         if (capture) {
