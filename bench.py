@@ -138,10 +138,11 @@ RBPF_DF_BYTES_PER_PARTICLE = 12 * RBPF_CELLS
 
 def rbpf_inputs(n_scans, seed=4):
     import numpy as np
-    import _oracle as orc
-    poses, twists = orc.circle_path(n_scans)
+    import _pkg
+    syn = _pkg.load().synthetic
+    poses, twists = syn.circle_path(n_scans)
     rng = np.random.default_rng(seed)
-    scans = [orc.room_scan(poses[i + 1], rng=rng) for i in range(n_scans)]
+    scans = [syn.room_scan(poses[i + 1], rng=rng) for i in range(n_scans)]
     return poses, twists, scans
 
 
@@ -175,7 +176,7 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
     scan.  At N > 1 GPUs the weights travel with one allgather per scan, every rank runs the identical walk and
     particles whose ancestor lives on another GPU migrate (ncclSend/ncclRecv)."""
     poses, twists, scans = rbpf_inputs(n_scans + warmup)
-    q = __import__("_oracle").pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]), motion_noise=RBPF_MOTION_NOISE)
+    q = pkg.synthetic.pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]), motion_noise=RBPF_MOTION_NOISE)
     if world > 1:
         f = pkg.bmapping.make_filter(q, particle_offset=rank * RBPF_N, particles_total=world * RBPF_N, device=local)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -338,8 +339,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
 
-    import _oracle as orc
-    prm = orc.SHIPPED
+    prm = pkg.synthetic.SHIPPED          # inputs only; the CPU checkers are imported by the cpu_baseline leg alone
     mppi = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
                     prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], HORIZON, DT, K_ROLLOUTS,
                     rollout_offset=rank * K_ROLLOUTS, rollouts_total=world * K_ROLLOUTS, device=local)

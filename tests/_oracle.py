@@ -14,13 +14,13 @@ REF_SO = os.environ.get("B2N_REF_SO", os.path.join(ROOT, "oracle", "_ref", "libr
 D = C.c_double
 nd = np.ctypeslib.ndpointer
 
-# shipped parameters: controller/config/mppi_params.yaml, nuturtle_description/config/diff_params.yaml
-SHIPPED = dict(wheel_radius=0.033, wheel_base=0.16, Q=(1e4, 1e4, 1.0), R=(0.1, 0.1), P1=(1e3, 1e3, 1e3),
-               lambda_=0.01, max_wheel_vel=6.35495, ul_var=0.9, ur_var=0.9)
-# well-conditioned set
-MILD = dict(wheel_radius=0.033, wheel_base=0.16, Q=(1.0, 1.0, 0.1), R=(0.1, 0.1), P1=(10.0, 10.0, 1.0),
-            lambda_=1.0, max_wheel_vel=6.35495, ul_var=0.9, ur_var=0.9)
-
+# synthetic inputs and shipped parameters live with the package (plain numpy, shared with bench.py and tools/)
+import importlib.util as _ilu  # noqa: E402
+_spec = _ilu.spec_from_file_location("b2n_synthetic", os.path.join(ROOT, "ros-turtlebot-navigation_b200", "synthetic.py"))
+_syn = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_syn)
+SHIPPED, MILD, PF_SHIPPED = _syn.SHIPPED, _syn.MILD, _syn.PF_SHIPPED
+pf_params, room_scan, circle_path, unicycle_step = _syn.pf_params, _syn.room_scan, _syn.circle_path, _syn.unicycle_step
 
 class _P(C.Structure):
     _fields_ = [("wheel_radius", D), ("wheel_base", D), ("Q", D * 3), ("R", D * 2), ("P1", D * 3),
@@ -210,28 +210,7 @@ class RefMppi:
             pass
 
 
-def unicycle_step(pose, ul, ur, dt, r=0.033, L=0.16):
-    """Plant used by closed-loop tests: exact arc integration of the wheel command over dt."""
-    x, y, th = pose
-    v = r / 2.0 * (ul + ur)
-    w = r / L * (ur - ul)
-    if abs(w) < 1e-12:
-        return (x + v * dt * np.cos(th), y + v * dt * np.sin(th), th)
-    return (x + v / w * (np.sin(th + w * dt) - np.sin(th)), y - v / w * (np.cos(th + w * dt) - np.cos(th)), th + w * dt)
-
-
 # =========================================================================================== RBPF
-# bmapping/launch/slam.launch:19-42 + bmapping/config/LDS_01_lidar.yaml, with the synthetic-bench
-# changes of SURVEY.md 8d (10 m map -> 200x200 cells, motion noise raised so that weights diverge)
-PF_SHIPPED = dict(
-    beam_min=0.0, beam_max=float(np.float32(np.deg2rad(360.0))), beam_delta=float(np.float32(np.deg2rad(1.0))),
-    range_min=0.12, range_max=3.5, z_hit=0.95, z_short=0.0, z_max=0.04, z_rand=0.01, sigma_hit=0.5,
-    resolution=0.05, xmin=-5.0, xmax=5.0, ymin=-5.0, ymax=5.0,
-    num_particles=40, k=50, srr=0.01, srt=0.02, str_=0.01, stt=0.02,
-    motion_noise=(1e-4, 1e-4, 1e-4), sample_range=(1e-4, 1e-4, 1e-4),
-    scan_min=1.0, scan_max=20.0, pose_min=1.0, pose_max=10.0, init_pose=(0.0, 0.0, 0.0))
-
-
 class _OPF(C.Structure):
     _fields_ = [("beam_min", C.c_float), ("beam_max", C.c_float), ("beam_delta", C.c_float), ("range_min", C.c_float),
                 ("range_max", C.c_float), ("z_hit", D), ("z_short", D), ("z_max", D), ("z_rand", D), ("sigma_hit", D),
@@ -239,13 +218,6 @@ class _OPF(C.Structure):
                 ("num_particles", C.c_int32), ("k", C.c_int32), ("srr", D), ("srt", D), ("str_", D), ("stt", D),
                 ("motion_noise", D * 3), ("sample_range", D * 3), ("scan_min", D), ("scan_max", D), ("pose_min", D),
                 ("pose_max", D), ("init_pose", D * 3)]
-
-
-def pf_params(**kw):
-    q = dict(PF_SHIPPED)
-    q.update(kw)
-    q["k"], q["num_particles"] = int(q["k"]), int(q["num_particles"])
-    return q
 
 
 _opf_bound = False
@@ -599,49 +571,3 @@ class RefGrid:
             pass
 
 
-# ------------------------------------------------------------------------------ synthetic world ---
-def room_scan(pose, half=2.5, boxes=((0.8, 1.4, -0.3, 0.4),), n_beams=360, beam_delta=np.deg2rad(1.0), sigma=0.01, rng=None,
-              range_max=3.5):
-    """Analytic ray cast from pose = (theta, x, y) in an axis-aligned square room of half-width `half` with
-    axis-aligned boxes (xlo, xhi, ylo, yhi); Gaussian range noise sigma (Gazebo lidar,
-    nuturtle_gazebo/urdf/diff_drive.gazebo.xacro:101-105); float32 ranges; beams past range_max read range_max + 1
-    (filtered by the range gate like an LDS-01 'inf')."""
-    th, x, y = pose
-    out = np.zeros(n_beams, dtype=np.float32)
-    for b in range(n_beams):
-        a = th + b * beam_delta
-        dx, dy = np.cos(a), np.sin(a)
-        best = np.inf
-        rects = [(-half, half, -half, half)] + list(boxes)
-        for (xl, xh, yl, yh) in rects:
-            for (px, horiz) in ((xl, False), (xh, False), (yl, True), (yh, True)):
-                if not horiz:
-                    if abs(dx) < 1e-12:
-                        continue
-                    t = (px - x) / dx
-                    q = y + t * dy
-                    ok = yl - 1e-12 <= q <= yh + 1e-12
-                else:
-                    if abs(dy) < 1e-12:
-                        continue
-                    t = (px - y) / dy
-                    q = x + t * dx
-                    ok = xl - 1e-12 <= q <= xh + 1e-12
-                if ok and t > 1e-9 and t < best:
-                    best = t
-        r = best + (rng.normal(0.0, sigma) if (rng is not None and sigma > 0) else 0.0)
-        out[b] = np.float32(r if r < range_max else range_max + 1.0)
-    return out
-
-
-def circle_path(n_scans, radius=0.5, step=0.05):
-    """Robot poses (theta, x, y) on a circle of `radius`, arc length `step` per scan, heading tangent; with the
-    per-scan body twist (w, vx, vy) that takes one pose to the next."""
-    poses, twists = [], []
-    dphi = step / radius
-    for i in range(n_scans + 1):
-        phi = i * dphi
-        poses.append((np.pi / 2 + phi, radius * np.cos(phi), radius * np.sin(phi)))
-    for i in range(n_scans):
-        twists.append((dphi, step, 0.0))
-    return np.array(poses), np.array(twists)

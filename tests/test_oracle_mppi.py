@@ -164,3 +164,30 @@ def test_philox_mode_is_shard_invariant():
         sh.setWaypoint(1, 0, 0)
         sh.newControls(0, 0, 0)
         assert np.array_equal(sh.get()["du"], du[off:off + 32])
+
+
+def test_mppi_noise_quad_known_answers_and_statistics():
+    """The MPPI perturbation generator (Philox4x32-10 -> four binary32 normals by an exact-operation Box-Muller) is a
+    CONVENTION of this repo shared by oracle/noise.hpp and csrc/common.cuh: pin it with known answers (bit patterns), so
+    that neither side can drift unnoticed, and check that it is a standard normal."""
+    import ctypes as C
+    L = orc.oracle_lib()
+    f = L.orc_philox_normal_quad_f32
+    f.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    f.restype = None
+    out = (C.c_float * 4)()
+    kat = {(42, 0x4D505049, 0, 0, 0): [1074173011, 1072889872, 3197487796, 3213492764],
+           (42, 0x4D505049, 7, 16383, 31): [3216721748, 1057485327, 3185289316, 1068932674],
+           (0xDEADBEEFCAFEF00D, 0x4D505049, 123456, 99, 5): [3210637932, 1076113122, 3192928633, 1047146036]}
+    for args, want in kat.items():
+        f(*args, out)
+        assert [int(np.float32(v).view(np.uint32)) for v in out] == want, args
+    z = []
+    for i in range(20000):
+        f(7, 0x4D505049, i % 50, i // 50, i % 13, out)
+        z.extend(out[:])
+    z = np.array(z, dtype=np.float64)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02 and np.max(np.abs(z)) < 5.78
+    assert abs(np.corrcoef(z[0::4], z[1::4])[0, 1]) < 0.03 and abs(np.corrcoef(z[0::4], z[2::4])[0, 1]) < 0.03
+    from scipy import stats
+    assert stats.kstest(z, "norm").pvalue > 1e-3

@@ -16,12 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _pkg  # noqa: E402
-import _oracle as orc  # noqa: E402
 
 ticks = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
 pkg = _pkg.load()
+orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED
 dt, hor, scan_every = 0.02, 0.64 * 2, 10          # 50 Hz control, T = 64 at dt = 0.02, 5 Hz lidar
 rng = np.random.default_rng(0)

@@ -2,8 +2,9 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import _pkg, _oracle as orc  # noqa: E402
+import _pkg  # noqa: E402
 pkg = _pkg.load()
+orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED
 m = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]), prm["lambda_"],
              prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], 0.64, 0.01, 16384)

@@ -5,8 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _pkg  # noqa: E402
-import _oracle as orc  # noqa: E402
 pkg = _pkg.load()
+orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 16384

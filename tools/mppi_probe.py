@@ -8,13 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _pkg  # noqa: E402
-import _oracle as orc  # noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 hor = float(sys.argv[2]) if len(sys.argv) > 2 else 0.64
 dt = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
 params = sys.argv[4] if len(sys.argv) > 4 else "shipped"
 pkg = _pkg.load()
+orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED if params == "shipped" else orc.MILD
 shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8), (4, 16, 7)]
 if os.environ.get("PROBE_SHAPES"):

@@ -9,13 +9,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _pkg  # noqa: E402
-import _oracle as orc  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 scans = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 hcap = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 icp = int(sys.argv[4]) if len(sys.argv) > 4 else 0     # 1: improved-proposal branch from the second scan on (Ticp = odometry increment)
 pkg = _pkg.load()
+orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 poses, twists = orc.circle_path(scans)
 rng = np.random.default_rng(4)
 f = pkg.bmapping.make_filter(orc.pf_params(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3)))
