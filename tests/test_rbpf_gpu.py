@@ -328,3 +328,34 @@ def test_unchanged_occupied_set_skips_the_distance_field_and_changes_nothing(gpu
             assert np.array_equal(f.occOrder(k), o.occ_order(k))
         assert rel(f.weights(), o.state()["weights"]) < 1e-9
     assert f.distanceFieldSkipped() == (scans - 1) * N
+
+
+def test_fifty_scans_match_oracle(gpu_pkg):
+    """>= 50 consecutive scans with the filter state carried (most of a lap of the circular path), every
+    scan compared: resampling decisions and ancestors bit-exact, weights / poses at 1e-9, maps of two particles and the
+    exported map equal."""
+    rng = np.random.default_rng(50)
+    N, scans = 16, 50
+    poses, twists = orc.circle_path(scans)
+    kw = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3))
+    f = make_gpu(gpu_pkg, **kw)
+    o = orc.OraclePf(**kw)
+    f.seed(50)
+    o.noise_philox(50)
+    n_res = 0
+    for i in range(scans):
+        scan = orc.room_scan(poses[i + 1], rng=rng)
+        assert o.slam(scan, twists[i], poses[i + 1], poses[i]) == 0
+        slam_gpu(gpu_pkg, f, scan, twists[i], poses[i + 1], poses[i])
+        neff_o, rs_o, anc_o = o.resample_info()
+        neff_g, rs_g, anc_g = f.resampleInfo()
+        assert (neff_g, rs_g) == (neff_o, rs_o) and np.array_equal(anc_g, anc_o), i
+        n_res += rs_o
+        so = o.state()
+        assert rel(f.weights(), so["weights"]) < 1e-9, i
+        assert np.max(np.abs(f.poses()[0] - so["poses"])) < 1e-9, i
+        if i % 7 == 0 or i == scans - 1:
+            for k in (0, N - 1):
+                assert_grid_equal(f.grid(k), o.grid(k))
+            assert np.array_equal(f.newMap(), o.new_map())
+    assert n_res >= 5
