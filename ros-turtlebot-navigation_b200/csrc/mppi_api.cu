@@ -2,6 +2,7 @@
 // Host side of controller::MPPI (reference: controller/src/controller/mppi.cpp:28-69,72-140).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -433,11 +434,16 @@ int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur)
   // word (about a microsecond after the store) instead of a stream synchronisation; every so often make sure the
   // stream has not failed
   volatile unsigned long long *seq = reinterpret_cast<volatile unsigned long long *>(h->h_out + 2);
+  const auto t_start = std::chrono::steady_clock::now();
   for (unsigned spins = 0; *seq != h->out_seq; spins++) {
     if ((spins & 0xFFFFu) == 0xFFFFu) {
       const cudaError_t e = cudaStreamQuery(h->stream);
       if (e == cudaSuccess) break;                  // finished: the word is visible by now
       if (e != cudaErrorNotReady) { set_error("stream failed while waiting for the controls: %s", cudaGetErrorString(e)); return B2N_ERR_CUDA; }
+      if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(60)) {
+        set_error("no controls after 60 s (a sharded job waits for every rank: is one of them gone?)");
+        return B2N_ERR_COMM;
+      }
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);

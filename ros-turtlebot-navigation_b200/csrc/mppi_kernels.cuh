@@ -574,8 +574,10 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kerne
     const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
     const unsigned long long *src = x.peer[x.rank] + (((size_t)par * x.nranks + r) * T + t) * kMppiXchgWords + w;
     unsigned long long got;
+    unsigned polls = 0;
     do {
       asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+      if (++polls == (1u << 27)) __trap();          // about a minute without the peer's word: fail loudly, not silently
     } while ((uint32_t)(got >> 32) != x.call_id);
     all[r][w] = (uint32_t)got;
   }
