@@ -359,3 +359,28 @@ def test_fifty_scans_match_oracle(gpu_pkg):
                 assert_grid_equal(f.grid(k), o.grid(k))
             assert np.array_equal(f.newMap(), o.new_map())
     assert n_res >= 5
+
+
+def test_largest_maps_and_other_scan_geometries(gpu_pkg):
+    """A 250 x 250 map (62 500 cells: 16-bit cell ids nearly exhausted, 62 bitmap columns per particle in tensor memory)
+    and a 180-beam, 2-degree scanner."""
+    rng = np.random.default_rng(9)
+    N, scans = 6, 3
+    poses, twists = orc.circle_path(scans)
+    kw = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3), xmin=-6.25, xmax=6.25, ymin=-6.25, ymax=6.25,
+              beam_delta=float(np.float32(np.deg2rad(2.0))))
+    f = make_gpu(gpu_pkg, **kw)
+    assert f.xsize == 250
+    o = orc.OraclePf(**kw)
+    f.seed(4)
+    o.noise_philox(4)
+    for i in range(scans):
+        scan = orc.room_scan(poses[i + 1], n_beams=180, beam_delta=np.deg2rad(2.0), rng=rng)
+        assert o.slam(scan, twists[i], poses[i + 1], poses[i]) == 0
+        slam_gpu(gpu_pkg, f, scan, twists[i], poses[i + 1], poses[i])
+        for k in (0, N - 1):
+            assert_grid_equal(f.grid(k), o.grid(k))
+            assert np.array_equal(f.occOrder(k), o.occ_order(k))
+        assert np.array_equal(f.resampleInfo()[2], o.resample_info()[2])
+        assert np.array_equal(f.newMap(), o.new_map())
+    assert rel(f.weights(), o.state()["weights"]) < 1e-9
