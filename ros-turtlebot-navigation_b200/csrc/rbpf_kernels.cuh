@@ -20,9 +20,14 @@
 //     ITERATION ORDER seeds the distance transform.
 //   * rays are applied in beam order, 32 cells of a ray at a time (cells of one ray are distinct; the k-th cell
 //     of the reference's Bresenham variants has a closed form), hash events replayed in lane order.
-//   * the distance field is the reference's order-dependent brushfire: binary heap (libstdc++ push_heap /
-//     pop_heap mechanics, ties included) and visit marks live in shared memory; every lane of the warp runs
-//     the heap code redundantly so that no intra-warp hand-off is needed; lanes 0-3 test the four neighbours.
+//   * the distance field is the reference's order-dependent brushfire: one serial chain of G heap steps per particle
+//     (libstdc++ push_heap / pop_heap mechanics, ties included).  One CTA per SM keeps 28 particles in flight (a single
+//     wave at 4096 particles): the heaps fill the shared memory, the visited bitmaps live in TENSOR MEMORY
+//     (tcgen05.ld / tcgen05.st as a scratchpad); a warp carries one particle, or two / four in lane groups under SIMT
+//     divergence; lanes 0-3 of a group test the four neighbours.  Particles whose occupied set did not change are skipped.
+//   * normalise / N_eff / low-variance walk run in the reference's sequential fp64 order on one warp (weights streamed
+//     32 at a time); resampling copies are one gather kernel - across GPUs it reads the ancestor's planes straight from
+//     the peer's HBM over NVLink (CUDA IPC mappings).
 #pragma once
 
 #include "common.cuh"
