@@ -694,8 +694,9 @@ struct HeapDev
     uint32_t a = sb;                                       // slot of index `second` = 0 ... the hole is entry `second`
     uint2 above = make_uint2(0u, 0u);                      // the entry now sitting in the hole's parent
     // (tried and measured slower in every lane-group configuration: loading the children pairs of both candidates one
-    // level ahead - more shared-memory wavefronts and issue slots than the latency it hides; eleven fully unrolled,
-    // predicated levels instead of the loop - 42.9 vs 39.7 ms)
+    // level ahead - 3 % faster with one chain per SM, slower with 28: the walk is bound by its dependent instructions,
+    // not by the shared-memory latency; eleven fully unrolled, predicated levels instead of the loop - 42.9 vs 39.7 ms;
+    // keeping the root in a register across steps with a peeled first level - 41.0 vs 39.7 ms)
     while (a < alim) {
       const uint32_t hole_a = a + 8u;
       a = 2u * a - K;
