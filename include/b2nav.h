@@ -256,6 +256,33 @@ int b2n_pf_p2p_init(b2n_pf *h, int rank, int nranks, const void *handles);
 /* particles received from / sent to other ranks by the last SLAM() */
 int b2n_pf_get_migration(const b2n_pf *h, int *received, int *sent);
 
+/* ================================================================================ scan matcher */
+
+/* SURVEY.md 8f row 2.  The reference takes its scan matcher from PCL (pcl::IterativeClosestPoint behind
+ * bmapping::ScanAlignment, cloud_alignment.cpp:28-80,160-223), which is neither vendored nor pinned; this is libb2nav's
+ * own point-to-point ICP with the reference's settings and wrapper semantics, parity-checked against
+ * oracle/icp_oracle.cpp only.  Its (success, T) pair is what b2n_pf_slam takes as (icp_ok, icp_pose). */
+typedef struct b2n_icp b2n_icp;
+
+typedef struct b2n_icp_params {
+  float beam_min, beam_max, beam_delta, range_min, range_max;   /* LaserProperties, sensor_model.hpp:63-76 */
+  int32_t max_iter;                                             /* cloud_alignment.cpp:21: 100 */
+  double max_correspondence_dist;                               /* :22: 0.5 */
+  double transformation_epsilon;                                /* :23: 1e-8 */
+  double euclidean_fitness_epsilon;                             /* :24: 1e-6 */
+  int32_t device;
+  int32_t max_beams;                                            /* capacity for scan length; 0 -> 1024 */
+} b2n_icp_params;
+
+int b2n_icp_create(const b2n_icp_params *params, b2n_icp **out);
+void b2n_icp_destroy(b2n_icp *h);
+/* bmapping::ScanAlignment::pclICPWrapper, cloud_alignment.cpp:37-72: the first call stores the scan and reports success
+ * with t untouched; later calls align the new scan (source) onto the stored one (target) from the initial guess
+ * t_init = (theta, x, y); on success t = (theta, x, y) of the transform and the new scan becomes the stored one. */
+int b2n_icp_align(b2n_icp *h, const float *scan, int n_beams, const double t_init[3], double t[3], int *success);
+/* iterations, correspondences and mean squared pair distance of the last alignment; kernel launches so far */
+int b2n_icp_stats(const b2n_icp *h, int *iterations, int *pairs, double *mse, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,10 @@ PROTOTYPES = {
     "b2n_pf_set_heap_capacity": (C.c_int, [_vp, C.c_int]),
     "b2n_pf_host_tables": (C.c_int, [_P(PfParams), _P(D), _vp, _sz, _vp, _sz, _P(C.c_int)]),
     "b2n_pf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b2n_icp_create": (C.c_int, [_vp, _P(_vp)]),
+    "b2n_icp_destroy": (None, [_vp]),
+    "b2n_icp_align": (C.c_int, [_vp, _vp, C.c_int, _P(D), _P(D), _P(C.c_int)]),
+    "b2n_icp_stats": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int), _P(D), _P(C.c_uint64)]),
     "b2n_pf_p2p_export": (C.c_int, [_vp, _vp]),
     "b2n_pf_p2p_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2n_pf_plan_migration": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _P(C.c_int), _vp, _sz, _P(C.c_int)]),
@@ -117,6 +121,12 @@ PROTOTYPES = {
 }
 
 _lib = None
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("beam_min", C.c_float), ("beam_max", C.c_float), ("beam_delta", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("max_iter", C.c_int32), ("max_correspondence_dist", D), ("transformation_epsilon", D),
+                ("euclidean_fitness_epsilon", D), ("device", C.c_int32), ("max_beams", C.c_int32)]
 
 
 def load_library():

@@ -7,6 +7,7 @@ reference.  GridMapper and LaserProperties only carry parameters here: the per-p
 Every numeric operation of SLAM() happens in the CUDA kernels; this file only marshals arguments.
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -57,6 +58,59 @@ class ScanAlignment:
         return self._ok, self._T
 
 
+class GpuScanAlignment(ScanAlignment):
+    """ScanAlignment whose matcher runs on the GPU (b2n_icp_*): libb2nav's own point-to-point ICP with the reference's
+    settings (cloud_alignment.cpp:20-25) and wrapper semantics (:37-72).  The reference's matcher is PCL's, which is
+    not pinned here - results are checked against oracle/icp_oracle.cpp, not against PCL."""
+
+    def __init__(self, props, Trs=None, *, max_iter=100, max_correspondence_dist=0.5, transformation_epsilon=1e-8,
+                 euclidean_fitness_epsilon=1e-6, device=-1, max_beams=0):
+        super().__init__(props, Trs)
+        self._lib = _capi.load_library()
+        p = _capi.IcpParams()
+        p.beam_min, p.beam_max, p.beam_delta, p.range_min, p.range_max = props.beam_min, props.beam_max, props.beam_delta, props.range_min, props.range_max
+        p.max_iter, p.max_correspondence_dist = int(max_iter), max_correspondence_dist
+        p.transformation_epsilon, p.euclidean_fitness_epsilon = transformation_epsilon, euclidean_fitness_epsilon
+        p.device, p.max_beams = int(device), int(max_beams)
+        h = C.c_void_p()
+        _capi.check(self._lib.b2n_icp_create(C.byref(p), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b2n_icp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def pclICPWrapper(self, T_init, beam_length):
+        scan = np.ascontiguousarray(beam_length, dtype=np.float32)
+        D3 = C.c_double * 3
+        Ti = (0.0, 0.0, 0.0) if T_init is None else tuple(T_init)
+        T, ok = D3(*self._T), C.c_int(0)
+        _capi.check(self._lib.b2n_icp_align(self._h, _capi.as_ptr(scan), scan.size, D3(*Ti), T, C.byref(ok)))
+        if ok.value:
+            self._T = (T[0], T[1], T[2])
+        return bool(ok.value), self._T
+
+    def stats(self):
+        """-> (iterations, correspondences, mean squared pair distance, kernel launches)"""
+        it, pairs, mse, launches = C.c_int(0), C.c_int(0), C.c_double(0), C.c_uint64(0)
+        _capi.check(self._lib.b2n_icp_stats(self._h, C.byref(it), C.byref(pairs), C.byref(mse), C.byref(launches)))
+        return it.value, pairs.value, mse.value, launches.value
+
+
+def icpInitGuess(cur_odom, prev_odom):
+    """particle_filter.cpp:602-612 -> (theta, x, y): the odometry difference (world-frame dx, dy, like the reference)"""
+    def npi(rad):                      # rigid2d::normalize_angle_PI, rigid2d.hpp:52-64
+        q = math.floor((rad + math.pi) / (2.0 * math.pi))
+        rad = (rad + math.pi) - q * 2.0 * math.pi
+        if rad < 0:
+            rad += 2.0 * math.pi
+        return rad - math.pi
+    return (npi(npi(cur_odom.theta) - npi(prev_odom.theta)), cur_odom.x - prev_odom.x, cur_odom.y - prev_odom.y)
+
+
 class ParticleFilter:
     """bmapping::ParticleFilter, particle_filter.hpp:112-144.
 
@@ -100,8 +154,8 @@ class ParticleFilter:
     def SLAM(self, scan, u, cur_odom, prev_odom):
         """particle_filter.cpp:141-251.  scan: float ranges; u: Twist2D; cur_odom / prev_odom: Pose."""
         scan = np.ascontiguousarray(scan, dtype=np.float32)
-        # icpInitGuess (particle_filter.cpp:602-612) feeds the matcher; the matcher itself is the caller's (PCL)
-        ok, T = self.scan_matcher.pclICPWrapper(None, scan)
+        # icpInitGuess, then the matcher, exactly where the reference calls them (particle_filter.cpp:150-153)
+        ok, T = self.scan_matcher.pclICPWrapper(icpInitGuess(cur_odom, prev_odom), scan)
         D3 = C.c_double * 3
         _capi.check(self._lib.b2n_pf_slam(self._h, _capi.as_ptr(scan), scan.size, D3(u.w, u.vx, u.vy),
                                           D3(cur_odom.theta, cur_odom.x, cur_odom.y), D3(prev_odom.theta, prev_odom.x, prev_odom.y),

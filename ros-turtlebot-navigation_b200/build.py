@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libb2nav.so")
 
 # source -> extra flags.  The RBPF unit is built with -fmad=false: its cell indices and resampling ancestors must
 # round like the reference's x86-64 build (no fused multiply-add), see csrc/rbpf_kernels.cuh.
-SOURCES = {"api_common.cu": [], "mppi_api.cu": [], "rbpf_api.cu": ["-fmad=false"]}
+SOURCES = {"api_common.cu": [], "mppi_api.cu": [], "rbpf_api.cu": ["-fmad=false"], "icp_api.cu": ["-fmad=false"]}
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 NVCC_FLAGS = [

@@ -571,3 +571,45 @@ class RefGrid:
             pass
 
 
+
+
+# ---- scan matcher -------------------------------------------------------------------------------------
+class _OICP(C.Structure):
+    _fields_ = [("beam_min", C.c_float), ("beam_max", C.c_float), ("beam_delta", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("max_iter", C.c_int32), ("max_corr_dist", D), ("transform_eps", D), ("fitness_eps", D)]
+
+
+class OracleIcp:
+    """oracle/icp_oracle.cpp: CPU statement of the scan matcher (ScanAlignment::pclICPWrapper semantics)."""
+
+    def __init__(self, max_iter=100, max_corr_dist=0.5, transform_eps=1e-8, fitness_eps=1e-6, **kw):
+        self.L = oracle_lib()
+        self.L.orc_icp_create.restype = C.c_void_p
+        self.L.orc_icp_create.argtypes = [C.POINTER(_OICP)]
+        self.L.orc_icp_destroy.argtypes = [C.c_void_p]
+        self.L.orc_icp_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(D), C.POINTER(D)]
+        self.L.orc_icp_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(D)]
+        q = pf_params(**kw)
+        p = _OICP(q["beam_min"], q["beam_max"], q["beam_delta"], q["range_min"], q["range_max"], max_iter, max_corr_dist,
+                  transform_eps, fitness_eps)
+        self.h = C.c_void_p(self.L.orc_icp_create(C.byref(p)))
+        self._T = (0.0, 0.0, 0.0)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_icp_destroy(self.h)
+            self.h = None
+
+    def pclICPWrapper(self, T_init, scan):
+        scan = np.ascontiguousarray(scan, dtype=np.float32)
+        Ti = (0.0, 0.0, 0.0) if T_init is None else tuple(T_init)
+        T = (D * 3)(*self._T)
+        ok = self.L.orc_icp_align(self.h, scan.ctypes.data, scan.size, (D * 3)(*Ti), T)
+        if ok:
+            self._T = (T[0], T[1], T[2])
+        return bool(ok), self._T
+
+    def stats(self):
+        it, pairs, mse = C.c_int(0), C.c_int(0), D(0)
+        self.L.orc_icp_stats(self.h, C.byref(it), C.byref(pairs), C.byref(mse))
+        return it.value, pairs.value, mse.value

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <vector>
 
 #include <bmapping/particle_filter.hpp>
@@ -25,7 +26,11 @@ int main(int argc, char **argv)
     // bmapping/launch/slam.launch + nuturtle_robot/config/LDS_01_lidar.yaml
     LaserProperties props(0.0f, 6.28319f, 0.0174533f, 0.12f, 3.5f, 0.95, 0.0, 0.04, 0.01, 0.5);
     GridMapper grid(0.05, -5.0, 5.0, -5.0, 5.0, props, Trs);
-    ScanAlignment aligner(props, Trs);
+    const bool gpu_matcher = argc > 6 && std::atoi(argv[6]) != 0;
+    ScanAlignment stub(props, Trs);
+    std::unique_ptr<GpuScanAlignment> gpu_aligner;
+    if (gpu_matcher) gpu_aligner.reset(new GpuScanAlignment(props, Trs));
+    ScanAlignment &aligner = gpu_matcher ? static_cast<ScanAlignment &>(*gpu_aligner) : stub;
     Transform2D robot_pose(Vector2D(x0, y0), th0);
     ParticleFilter pf(num_particles, 50, 0.001, 0.001, 0.001, 0.001, 2e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1.0, 20.0, 1.0, 10.0, aligner,
                       robot_pose, grid);

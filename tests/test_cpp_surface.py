@@ -80,8 +80,10 @@ def test_slam_surface_compiles_against_reference_rigid2d(bindir):
 
 
 @pytest.mark.gpu
-def test_slam_cpp_equals_ctypes_path(bindir, gpu_pkg):
-    """bmapping::ParticleFilter through the C++ header and through the ctypes mirror: same robot state, same map."""
+@pytest.mark.parametrize("gpu_matcher", [0, 1])
+def test_slam_cpp_equals_ctypes_path(bindir, gpu_pkg, gpu_matcher):
+    """bmapping::ParticleFilter through the C++ header and through the ctypes mirror: same robot state, same map -
+    with the stand-in matcher (motion-model branch) and with GpuScanAlignment (improved-proposal branch)."""
     import numpy as np
     import _oracle as orc
     exe = _compile("slam_node_like.cpp", str(bindir / "slam_node_like_gpu"))
@@ -94,7 +96,7 @@ def test_slam_cpp_equals_ctypes_path(bindir, gpu_pkg):
         lines.append(" ".join(repr(float(v)) for v in (*twists[i], *poses[i + 1], *poses[i])))
         lines.append(" ".join(repr(float(v)) for v in scans[i]))
     th0, x0, y0 = poses[0]
-    r = subprocess.run([exe, str(N), "1", repr(float(x0)), repr(float(y0)), repr(float(th0))], input="\n".join(lines) + "\n",
+    r = subprocess.run([exe, str(N), "1", repr(float(x0)), repr(float(y0)), repr(float(th0)), str(gpu_matcher)], input="\n".join(lines) + "\n",
                        capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     got = [ln.split() for ln in r.stdout.strip().splitlines()]
@@ -102,6 +104,8 @@ def test_slam_cpp_equals_ctypes_path(bindir, gpu_pkg):
                                                    sample_range=(1e-3, 1e-3, 1e-3), srr=0.001, srt=0.001, str_=0.001, stt=0.001,
                                                    beam_max=6.28319, beam_delta=0.0174533))
     f.seed(1)
+    if gpu_matcher:
+        f.scan_matcher = gpu_pkg.bmapping.GpuScanAlignment(f.scan_matcher.props, None)
     for i in range(n_scans):
         f.SLAM(scans[i], gpu_pkg.Twist2D(*twists[i]), gpu_pkg.Pose(*poses[i + 1]), gpu_pkg.Pose(*poses[i]))
         m = f.newMap().astype(np.int64)

@@ -23,11 +23,18 @@ if hcap:
     f.setHeapCapacity(hcap)
 f.seed(1)
 f.setKernelTiming(True)
+if icp == 2:                                   # 2: the GPU scan matcher in the scan_matcher slot
+    f.scan_matcher = pkg.bmapping.GpuScanAlignment(f.scan_matcher.props, None)
 for i in range(scans):
     scan = orc.room_scan(poses[i + 1], rng=rng)
-    if icp and i > 0:
+    if icp == 1 and i > 0:
         w, d = twists[i][0], twists[i][1]
         f.scan_matcher.setResult(True, (w, d * np.cos(w / 2), d * np.sin(w / 2)))
+    if icp == 2:                               # time a second matcher on the same scan sequence
+        m = pkg.bmapping.GpuScanAlignment(f.scan_matcher.props, None) if i == 0 else m
+        t1 = time.perf_counter()
+        m.pclICPWrapper((0.0, 0.0, 0.0), scan)
+        print("   matcher: %.1f us for pclICPWrapper (host wall), (iterations, pairs, mse, launches) = %s" % ((time.perf_counter() - t1) * 1e6, m.stats()))
     t0 = time.perf_counter()
     f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
     wall = (time.perf_counter() - t0) * 1e3
