@@ -696,7 +696,11 @@ struct HeapDev
     // (tried and measured slower in every lane-group configuration: loading the children pairs of both candidates one
     // level ahead - 3 % faster with one chain per SM, slower with 28: the walk is bound by its dependent instructions,
     // not by the shared-memory latency; eleven fully unrolled, predicated levels instead of the loop - 42.9 vs 39.7 ms;
-    // keeping the root in a register across steps with a peeled first level - 41.0 vs 39.7 ms)
+    // keeping the root in a register across steps with a peeled first level - 41.0 vs 39.7 ms; a speculative walk that
+    // takes log2(GL) levels per round - every lane of the group loads the children pair of one node below the hole, a
+    // ballot of the winners tells each lane whether it is on the path, the path's lanes move their winners up at once -
+    // bit-exact, but 42.8 vs 40.7 ms: three rounds of LDS.128 + two ballots + two shuffles cost more than nine levels
+    // of eleven instructions; waiting for the bitmap's tcgen05.st only before the next step's tcgen05.ld - no change)
     while (a < alim) {
       const uint32_t hole_a = a + 8u;
       a = 2u * a - K;
