@@ -1008,6 +1008,7 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
     uint32_t it = 0;
     while (__any_sync(kFullMask, H.len > 0)) {
       const bool on = H.len > 0;
+      __syncwarp();                                                       // heap and window accesses of the previous step are done in every lane
       const uint2 top = lds64(H.sb + 8u);                                 // Q.top(), :399
       const int ci = (int)(top.x >> 24), cj = (int)((top.x >> 16) & 0xFFu), si = (int)((top.x >> 8) & 0xFFu), sj = (int)(top.x & 0xFFu);
       const int ni = ci + dI, nj = cj + dJ;
