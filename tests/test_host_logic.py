@@ -33,6 +33,12 @@ def test_no_cpu_path(pkg):
     with pytest.raises(pkg.B2NError) as e:
         pkg.bmapping.make_filter(orc.pf_params(num_particles=4))
     assert e.value.code == -2
+    q = orc.pf_params()
+    props = pkg.bmapping.LaserProperties(q["beam_min"], q["beam_max"], q["beam_delta"], q["range_min"], q["range_max"],
+                                         q["z_hit"], q["z_short"], q["z_max"], q["z_rand"], q["sigma_hit"])
+    with pytest.raises(pkg.B2NError) as e:
+        pkg.bmapping.GpuScanAlignment(props, None)
+    assert e.value.code == -2 and "no CPU path" in str(e.value)
 
 
 def _host_tables(pkg, q, n_beams=360):
