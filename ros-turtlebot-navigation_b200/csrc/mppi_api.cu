@@ -256,7 +256,7 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   u.merged = h->d_merged;
   if (h->nranks > 1 && h->p2p_ready) {
     // merge + exchange over NVLink peer memory + update in one kernel (mppi_exchange_update_kernel)
-    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
+    u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 0;
     MppiXchgArgs xa;
     std::memset(&xa, 0, sizeof(xa));
     for (int r = 0; r < h->nranks; r++) xa.peer[r] = static_cast<unsigned long long *>(h->peer_base[r]);
@@ -284,13 +284,13 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   }
   if (h->nranks > 1) {
     // local merge -> one allgather of [T][6] doubles -> identical update on every rank
-    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 1;
+    u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 1;
     if (int rc = launch_update(h, u)) return rc;
     ncclResult_t r = ncclAllGather(h->d_merged, h->d_gathered, (size_t)h->T * 6, ncclDouble, h->comm, h->stream);
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
-    u.partials = h->d_gathered; u.n_partials = h->nranks; u.merge_only = 0;
+    u.partials = h->d_gathered; u.n_partials = h->nranks; u.p_stride = 6 * h->T; u.t_stride = 6; u.merge_only = 0;
   } else {
-    u.partials = h->d_partials; u.n_partials = h->grid; u.merge_only = 0;
+    u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 0;
   }
   if (int rc = launch_update(h, u)) return rc;
 
@@ -567,7 +567,7 @@ int b2n_mppi_get_partials(b2n_mppi *h, double *out, size_t count)
   if (int rc = set_device(h)) return rc;
   MppiUpdateArgs u;
   std::memset(&u, 0, sizeof(u));
-  u.T = h->T; u.inv_lambda = 1.0 / h->p.lambda; u.partials = h->d_partials; u.n_partials = h->grid;
+  u.T = h->T; u.inv_lambda = 1.0 / h->p.lambda; u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid;
   u.merge_only = 1; u.merged = h->d_merged;
   if (int rc = launch_update(h, u)) return rc;
   return copy_out(h, out, h->d_merged, count * sizeof(double));

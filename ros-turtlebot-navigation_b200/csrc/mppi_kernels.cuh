@@ -56,12 +56,13 @@ struct MppiArgs
   const double *ext;       // [K][T][2] or null
   double *J_out;           // [K][T] (capture)
   double *du_out;          // [K][T][2] (capture)
-  double *partials;        // [gridDim.x][T][6]
+  double *partials;        // [T][gridDim.x][6]: a step's partials of all CTAs are contiguous for the CTA that merges them
 };
 
 struct MppiUpdateArgs
 {
-  const double *partials;  // [n_partials][T][6]
+  const double *partials;  // partial p of step t at partials + p * p_stride + t * t_stride (doubles):
+  int p_stride, t_stride;  //   CTA partials [T][n][6]: (6, 6 n);  gathered per-rank results [n][T][6]: (6 T, 6)
   int n_partials, T, merge_only;
   double inv_lambda, k_total, umax;
   double uinit[2];
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 && NW != 7 ? 3 
       for (int w = 0; w < kMppiWarps; w++)
 #pragma unroll
         for (int j = 0; j < 5; j++) v[j] += ssum[((ss * kMppiWarps + w) * 5 + j) * G + gg];
-      double *out = a.partials + ((size_t)blockIdx.x * T + t) * 6;
+      double *out = a.partials + ((size_t)t * gridDim.x + blockIdx.x) * 6;
       reinterpret_cast<double2 *>(out)[0] = make_double2(m, v[0]);
       reinterpret_cast<double2 *>(out)[1] = make_double2(v[1], v[2]);
       reinterpret_cast<double2 *>(out)[2] = make_double2(v[3], v[4]);
@@ -424,13 +425,14 @@ constexpr int kMppiUpdateThreads = 128;
 
 // merge of the step's partials by one CTA: minimum first, then every partial rescaled once (independent
 // exponentials), plain sums.  The result is valid in thread 0.
-__device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int T, int t, double inv_lambda, double &m,
+__device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int p_stride, int t_stride, int t, double inv_lambda, double &m,
                                                  double &S, double &A, double &B, double &DL, double &DR)
 {
   constexpr int kPer = 4;                                   // partials held in registers per thread (one L2 round trip)
   __shared__ double red[kMppiUpdateThreads / 32][6];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  const double *base = partials + (size_t)t * t_stride;
   double2 c0[kPer], c1[kPer], c2[kPer];
   m = inf;
 #pragma unroll
@@ -438,12 +440,12 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
     const int p = threadIdx.x + i * kMppiUpdateThreads;
     c0[i] = make_double2(inf, 0.0); c1[i] = make_double2(0.0, 0.0); c2[i] = make_double2(0.0, 0.0);
     if (p < n_partials) {
-      const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
+      const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
       c0[i] = c[0]; c1[i] = c[1]; c2[i] = c[2];
     }
     m = fmin(m, c0[i].x);
   }
-  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, partials[((size_t)p * T + t) * 6]);
+  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, base[(size_t)p * p_stride]);
   m = warp_min(m);
   if (lane == 0) red[warp][0] = m;
   __syncthreads();
@@ -460,7 +462,7 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
     DL += c2[i].x; DR += c2[i].y;
   }
   for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) {
-    const double2 *c = reinterpret_cast<const double2 *>(partials + ((size_t)p * T + t) * 6);
+    const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
     const double2 d0 = c[0], d1 = c[1], d2 = c[2];
     if (d0.x != inf) {
       const double f = (d0.x == m) ? 1.0 : mppi_exp_neg((m - d0.x) * inv_lambda);
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   // the next call's rollout grid may be scheduled now (its prologue overlaps this kernel; it waits before the plan)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
-  mppi_block_merge(a.partials, a.n_partials, a.T, t, a.inv_lambda, m, S, A, B, DL, DR);
+  mppi_block_merge(a.partials, a.n_partials, a.p_stride, a.t_stride, t, a.inv_lambda, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
   if (a.merge_only) {
     double *o = a.merged + (size_t)t * 6;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kerne
   asm volatile("griddepcontrol.wait;" ::: "memory");                 // programmatic dependent launch, as in mppi_update_kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
-  mppi_block_merge(a.partials, a.n_partials, T, t, a.inv_lambda, m, S, A, B, DL, DR);
+  mppi_block_merge(a.partials, a.n_partials, a.p_stride, a.t_stride, t, a.inv_lambda, m, S, A, B, DL, DR);
   if (threadIdx.x == 0) {
     const double v[6] = {m, S, A, B, DL, DR};
 #pragma unroll
