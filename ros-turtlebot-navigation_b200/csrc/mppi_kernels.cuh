@@ -584,16 +584,24 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kerne
     all[r][w] = (uint32_t)got;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  // fold the nranks results in rank order (identical on every rank).  The rescale factors are independent of one
+  // another: thread r computes rank r's (one exponential each, side by side), thread 0 then runs the ordered sums -
+  // the same operations in the same order as a serial fold, without nranks exponentials back to back
+  __shared__ double fac[kMppiMaxRanks];
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
   auto val = [&](int r, int i) { return __hiloint2double((int)all[r][2 * i + 1], (int)all[r][2 * i]); };
   m = inf;
   for (int r = 0; r < x.nranks; r++) m = fmin(m, val(r, 0));
+  if ((int)threadIdx.x < x.nranks) {
+    const double mr = val((int)threadIdx.x, 0);
+    fac[threadIdx.x] = (mr == inf) ? 0.0 : (mr == m) ? 1.0 : mppi_exp_neg((m - mr) * a.inv_lambda);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   S = A = B = DL = DR = 0.0;
   for (int r = 0; r < x.nranks; r++) {
-    const double mr = val(r, 0);
-    if (mr != inf) {
-      const double f = (mr == m) ? 1.0 : mppi_exp_neg((m - mr) * a.inv_lambda);
+    if (val(r, 0) != inf) {
+      const double f = fac[r];
       S = fma(val(r, 1), f, S); A = fma(val(r, 2), f, A); B = fma(val(r, 3), f, B);
     }
     DL += val(r, 4); DR += val(r, 5);
