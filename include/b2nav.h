@@ -118,6 +118,15 @@ int b2n_mppi_set_state_ring(b2n_mppi *h, int n);
 /* kernels launched by this handle since creation, and average device time (ms) of the rollout
  * kernel measured with CUDA events on the launching stream since the last call to this function */
 int b2n_mppi_launch_count(const b2n_mppi *h, uint64_t *launches);
+/* *fast = 1 when the last call ran the production (FAST) instantiation of the kernel, 0 for the generic one (capture taps,
+ * caller-supplied noise, horizons that leave lanes partially filled): lets a parity test prove which one it checked */
+int b2n_mppi_last_variant(const b2n_mppi *h, int *fast);
+/* tuning hook (B2N_MPPI_DEBUG_TIMES=1 at create): globaltimer stamps [grid][8] of every CTA of the last call: loop start, loop end,
+ * CTA partial written, group ticket drawn, group merged, grid ticket drawn, grid merged, plan published (0 where a CTA left earlier) */
+int b2n_mppi_debug_times(b2n_mppi *h, unsigned long long *out, size_t count, int *grid);
+/* test hook: the Box-Muller stage of the perturbation generator alone, z[2 i], z[2 i + 1] for the first words
+ * (first + i) << 9, i < count (the 2^23 values cover every radius the generator can produce) and one second word rb */
+int b2n_test_box_muller(uint32_t first, uint32_t count, uint32_t rb, float *z);
 int b2n_mppi_set_kernel_timing(b2n_mppi *h, int on);
 int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples);
 /* bench hook: the rollout kernel alone, `launches` times back to back on the handle's stream between two CUDA events
@@ -139,6 +148,11 @@ int b2n_mppi_comm_init(b2n_mppi *h, int rank, int nranks, const void *unique_id1
  * path once initialised. */
 int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64);
 int b2n_mppi_p2p_init(b2n_mppi *h, int rank, int nranks, const void *handles);
+/* The same wiring for ranks that are handles of ONE process (several GPUs driven by one process, or - in the tests - two
+ * ranks sharing one GPU on separate streams): b2n_mppi_p2p_export on every handle, then the device addresses of all
+ * areas (b2n_mppi_p2p_area) in rank order.  The handles must outlive each other's use. */
+int b2n_mppi_p2p_area(b2n_mppi *h, void **area);
+int b2n_mppi_p2p_init_local(b2n_mppi *h, int rank, int nranks, void *const *areas);
 
 /* ======================================================================================== RBPF */
 

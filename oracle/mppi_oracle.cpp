@@ -282,6 +282,11 @@ void orc_philox_normal_quad_f32(uint64_t seed, uint32_t domain, uint32_t call, u
 {
   orc::philox_normal_quad_f32(seed, domain, call, stream, index, z);
 }
+// the Box-Muller stage alone over a range of first words (ra = (first + i) << 9, every possible radius), one second word
+void orc_box_muller_range(uint32_t first, uint32_t count, uint32_t rb, float *z)
+{
+  for (uint32_t i = 0; i < count; i++) orc::box_muller_f32((first + i) << 9, rb, &z[2 * (size_t)i], &z[2 * (size_t)i + 1]);
+}
 void orc_philox_normal_pair(uint64_t seed, uint32_t domain, uint32_t call, uint32_t stream, uint32_t index, double *z)
 {
   orc::philox_normal_pair(seed, domain, call, stream, index, &z[0], &z[1]);

@@ -75,6 +75,9 @@ PROTOTYPES = {
     "b2n_mppi_set_stream": (C.c_int, [_vp, _vp]),
     "b2n_mppi_set_state_ring": (C.c_int, [_vp, C.c_int]),
     "b2n_mppi_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "b2n_mppi_last_variant": (C.c_int, [_vp, _P(C.c_int)]),
+    "b2n_mppi_debug_times": (C.c_int, [_vp, _vp, _sz, _P(C.c_int)]),
+    "b2n_test_box_muller": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "b2n_mppi_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "b2n_mppi_kernel_time": (C.c_int, [_vp, _P(D), _P(C.c_int)]),
     "b2n_mppi_time_rollout": (C.c_int, [_vp, D, D, D, C.c_int, _P(D)]),
@@ -82,6 +85,8 @@ PROTOTYPES = {
     "b2n_mppi_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2n_mppi_p2p_export": (C.c_int, [_vp, C.c_int, _vp]),
     "b2n_mppi_p2p_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b2n_mppi_p2p_area": (C.c_int, [_vp, _P(_vp)]),
+    "b2n_mppi_p2p_init_local": (C.c_int, [_vp, C.c_int, C.c_int, _P(_vp)]),
     "b2n_pf_create": (C.c_int, [_P(PfParams), _P(_vp)]),
     "b2n_pf_destroy": (None, [_vp]),
     "b2n_pf_slam": (C.c_int, [_vp, _vp, C.c_int, _P(D), _P(D), _P(D), C.c_int, _P(D)]),

@@ -136,6 +136,20 @@ class MPPI:
     def setStateRing(self, n):
         _capi.check(self._lib.b2n_mppi_set_state_ring(self._h, int(n)))
 
+    def lastVariant(self):
+        """which instantiation of the kernel the last call ran: "fast" (production) or "generic" (taps / external noise / ragged horizon)"""
+        f = C.c_int()
+        _capi.check(self._lib.b2n_mppi_last_variant(self._h, C.byref(f)))
+        return "fast" if f.value else "generic"
+
+    def debugTimes(self):
+        """tuning: [grid][8] globaltimer stamps of the last call (needs B2N_MPPI_DEBUG_TIMES=1 when the handle was made)"""
+        out = np.zeros(24 * 4096, dtype=np.uint64)
+        g = C.c_int()
+        _capi.check(self._lib.b2n_mppi_debug_times(self._h, _capi.as_ptr(out), out.size, C.byref(g)))
+        n = g.value + self.steps
+        return out[:24 * n].reshape(n, 24)
+
     def launchCount(self):
         n = C.c_uint64()
         _capi.check(self._lib.b2n_mppi_launch_count(self._h, C.byref(n)))
@@ -165,6 +179,16 @@ class MPPI:
         """handles: the nranks x 64 bytes of every rank's p2pExport(), in rank order"""
         buf = C.create_string_buffer(bytes(handles), 64 * int(nranks))
         _capi.check(self._lib.b2n_mppi_p2p_init(self._h, int(rank), int(nranks), buf))
+
+    def p2pArea(self):
+        a = C.c_void_p()
+        _capi.check(self._lib.b2n_mppi_p2p_area(self._h, C.byref(a)))
+        return a.value
+
+    def p2pInitLocal(self, rank, nranks, areas):
+        """ranks that live in this process: areas = p2pArea() of every rank's handle, in rank order"""
+        arr = (C.c_void_p * int(nranks))(*areas)
+        _capi.check(self._lib.b2n_mppi_p2p_init_local(self._h, int(rank), int(nranks), arr))
 
     def commInit(self, rank, nranks, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)

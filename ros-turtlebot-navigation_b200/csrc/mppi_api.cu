@@ -36,15 +36,24 @@ struct b2n_mppi
   int cur = 0;
   float *d_states = nullptr;             // [ring][K][T][3]
   int ring = 1, ring_pos = 0, last_slot = 0;
-  double *d_partials = nullptr;          // [grid][T][6]
+  double *d_partials = nullptr;          // [T][grid][6]
+  unsigned long long *d_sync = nullptr;  // [2] fused calls: rollout CTAs counted in, plan steps completed (both monotonic)
+  unsigned long long fused_calls = 0;    // fused calls enqueued so far
+  unsigned long long *d_dbg = nullptr;   // [grid][8] stage timestamps, B2N_MPPI_DEBUG_TIMES=1 (tuning runs)
+  int last_fast = 0;                     // the last call ran the FAST instantiation
+  // the variates of a call, drawn ahead by mppi_noise_kernel behind the previous call: two buffers [K][T/2] float4
+  float4 *d_z[2] = {nullptr, nullptr};
+  long long z_call[2] = {-1, -1};        // the call number whose variates a buffer holds (-1: none)
+  uint64_t z_seed[2] = {0, 0};
+  bool noise_ahead = true;               // B2N_MPPI_NOISE_AHEAD=0: draw a call's variates in front of the call instead of behind the previous one
   double *d_merged = nullptr;            // [T][6]
   double *d_gathered = nullptr;          // [nranks][T][6]
   double *d_stepstats = nullptr;         // [T][2]
   double *h_out = nullptr;               // pinned, mapped [2]: the update kernel writes the controls here
   double *d_out_host = nullptr;          // device view of h_out
   unsigned long long out_seq = 0;        // sequence number of the last enqueued call (completion word in h_out[2])
-  bool use_pdl = true;                   // programmatic dependent launch of rollout -> update -> next rollout (trigger after the rollout
-                                         // loop, so dependents never take residency from it): 30.7 -> 24.7 us per call; B2N_MPPI_PDL=0 turns it off
+  bool use_pdl = true;                   // programmatic dependent launch of call -> next call (trigger after the rollout loop, so
+                                         // dependents never take residency from it); B2N_MPPI_PDL=0 turns it off
   double *d_ext = nullptr;               // [K][T][2]
   bool ext_armed = false;
   int capture = 0;
@@ -63,7 +72,7 @@ struct b2n_mppi
   size_t xchg_bytes = 0, xchg_flag_offset = 0;
   int xchg_nranks = 0;
   std::vector<void *> peer_base;         // mapped peer areas (own entry = xchg)
-  bool p2p_ready = false;
+  bool p2p_ready = false, p2p_local = false;   // local: the peers are handles of this process (plain device pointers, nothing to close)
   unsigned long long xchg_call = 0;
 
   // accounting
@@ -77,21 +86,27 @@ struct b2n_mppi
 namespace
 {
 
-// (S, G, NW) = steps per lane, lanes per rollout, warps per CTA; G * S >= T.  The table below is every shape that is built.
+// (S, G, NW) = steps per lane, lanes per rollout, warps per CTA; G * S >= T.  The table below is every shape that is built,
+// each as three instantiations: generic (taps, external noise, partial lanes, runtime obstacle switch), FAST and FAST + obstacle term.
 template <int S, int G, int NW>
 cudaError_t configure_shape(b2n_mppi *h)
 {
-  h->smem = mppi_rollout_smem(S, G, NW);
-  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  // the generic variant decides about the obstacle term at run time: its shared memory always includes the tile
+  h->smem = mppi_rollout_smem(S, G, NW, true, false);
+  cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  int per_sm = 0, per_sm_fast = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false, NW>, NW * 32, h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, mppi_rollout_kernel<S, G, true, NW>, NW * 32, h->smem);
+  int per_sm = 0, per_sm_fast = 0, per_sm_obs = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false, false, NW>, NW * 32, h->smem);
   if (e != cudaSuccess) return e;
-  per_sm = std::max(per_sm, per_sm_fast);     // the partials buffer is sized for the larger grid; both variants stride by gridDim
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, mppi_rollout_kernel<S, G, true, false, NW>, NW * 32, mppi_rollout_smem(S, G, NW, false, true));
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_obs, mppi_rollout_kernel<S, G, true, true, NW>, NW * 32, mppi_rollout_smem(S, G, NW, true, true));
+  if (e != cudaSuccess) return e;
+  per_sm = std::max(per_sm, std::max(per_sm_fast, per_sm_obs));     // the partials buffer is sized for the largest grid; every variant strides by gridDim
   if (per_sm < 1) per_sm = 1;
   // persistent grid: every SM filled to its residency limit (an evenly divided but smaller grid measured slower:
   // SMs holding one CTA more than their neighbours set the pace)
@@ -101,9 +116,7 @@ cudaError_t configure_shape(b2n_mppi *h)
   return cudaSuccess;
 }
 
-// (7-warp CTAs, four per SM, divide K = 16384 into equal passes - measured no faster than 8-warp CTAs (22.2 vs 20.5 us):
-// the kernel is bound by the dependent instruction stream of a pass, not by the half-empty last pass; not instantiated)
-#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8) X(4, 16, 7)
+#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8) X(4, 16, 10) X(4, 16, 20) X(4, 32, 10) X(4, 32, 20)
 
 cudaError_t configure(b2n_mppi *h)
 {
@@ -114,11 +127,11 @@ cudaError_t configure(b2n_mppi *h)
 }
 
 template <class Kernel>
-void launch_rollout_kernel(b2n_mppi *h, Kernel kernel, int threads, const MppiArgs &a)
+void launch_rollout_kernel(b2n_mppi *h, Kernel kernel, int threads, size_t smem, const MppiArgs &a)
 {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)h->grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = h->smem; cfg.stream = h->stream;
+  cfg.gridDim = dim3((unsigned)(h->grid + (a.tail ? h->T : 0))); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -126,13 +139,15 @@ void launch_rollout_kernel(b2n_mppi *h, Kernel kernel, int threads, const MppiAr
   cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-void launch_rollout(b2n_mppi *h, const MppiArgs &a, bool fast)
+// variant: 0 generic, 1 FAST, 2 FAST with the obstacle term
+void launch_rollout(b2n_mppi *h, const MppiArgs &a, int variant)
 {
-#define X(S_, G_, W_)                                                                                           \
-  if (h->S == S_ && h->G == G_ && h->NW == W_) {                                                                \
-    if (fast) launch_rollout_kernel(h, mppi_rollout_kernel<S_, G_, true, W_>, W_ * 32, a);                      \
-    else launch_rollout_kernel(h, mppi_rollout_kernel<S_, G_, false, W_>, W_ * 32, a);                          \
-    return;                                                                                                     \
+#define X(S_, G_, W_)                                                                                                           \
+  if (h->S == S_ && h->G == G_ && h->NW == W_) {                                                                                \
+    if (variant == 1) launch_rollout_kernel(h, mppi_rollout_kernel<S_, G_, true, false, W_>, W_ * 32, mppi_rollout_smem(S_, G_, W_, false, true), a);   \
+    else if (variant == 2) launch_rollout_kernel(h, mppi_rollout_kernel<S_, G_, true, true, W_>, W_ * 32, mppi_rollout_smem(S_, G_, W_, true, true), a);  \
+    else launch_rollout_kernel(h, mppi_rollout_kernel<S_, G_, false, false, W_>, W_ * 32, mppi_rollout_smem(S_, G_, W_, true, false), a);               \
+    return;                                                                                                                     \
   }
   B2N_MPPI_SHAPES(X)
 #undef X
@@ -145,8 +160,8 @@ void pick_shape(int T, int &S, int &G, int &NW)
   NW = 8;
   if (T <= 16) { S = 2; G = 8; }
   else if (T <= 32) { S = 4; G = 8; }
-  else if (T <= 64) { S = 4; G = 16; }
-  else if (T <= 128) { S = 4; G = 32; }
+  else if (T <= 64) { S = 4; G = 16; NW = 10; }      // 2 CTAs x 10 warps per SM at 96 registers: 20 warps, no spill traffic in the loop,
+  else if (T <= 128) { S = 4; G = 32; NW = 10; }     //   and K = 16384 divides into 2.8 passes per warp (8-warp CTAs: 2.3, a third pass for a third of them)
   else { S = 8; G = 32; }
   if (const char *env = std::getenv("B2N_MPPI_SHAPE")) {
     int s = 0, g = 0, w = 8;
@@ -176,12 +191,19 @@ MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
   for (int i = 0; i < 3; i++) { a.Q[i] = p.Q[i]; a.P1[i] = p.P1[i]; a.xd[i] = h->xd[i]; }
   a.R[0] = p.R[0]; a.R[1] = p.R[1];
   a.inv_lambda = 1.0 / p.lambda;
+  a.cut_lambda = 708.0 * p.lambda;
   a.sigL = std::sqrt(p.ul_var);       // mppi.cpp:176-177
   a.sigR = std::sqrt(p.ur_var);
   a.x0[0] = x; a.x0[1] = y; a.x0[2] = theta;   // mppi.cpp:75-76
   a.cos0 = std::cos(theta); a.sin0 = std::sin(theta);
+  a.ks3 = -1.6666666666666666e-01; a.ks5 = 8.3333333333333332e-03; a.ks7 = -1.9841269841269841e-04; a.ks9 = 2.7557319223985893e-06;
+  a.kc2 = -0.5; a.kc4 = 4.1666666666666664e-02; a.kc6 = -1.3888888888888889e-03; a.kc8 = 2.4801587301587302e-05; a.kc10 = -2.7557319223985888e-07;
   a.T = h->T; a.K = h->K; a.k_offset = p.rollout_offset;
-  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.call = h->call;
+  a.call = h->call;
+  for (int r = 0; r < 10; r++) {
+    a.key0[r] = (uint32_t)h->seed + (uint32_t)r * 0x9E3779B9u;
+    a.key1[r] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
   a.external_noise = h->ext_armed ? 1 : 0;
   a.capture = h->capture;
   a.tma_store = h->tma_store ? 1 : 0;
@@ -190,19 +212,90 @@ MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
   a.obs_xmax = h->obs_xmin + h->obs_xsize * h->obs_res;
   a.obs_ymax = h->obs_ymin + h->obs_ysize * h->obs_res;
   a.obs_weight = h->obs_weight; a.obs_d0 = h->obs_d0; a.obs_off = h->obs_off; a.obs_dist = h->d_obs;
+  // the tile of the field staged through TMA: kMppiObsTile cells square around the start pose's cell, clamped into the
+  // field, its first column a multiple of four cells (16-byte granules of the bulk copies)
+  a.obs_ti0 = a.obs_tj0 = -1;
+  if (h->obs_on && h->obs_xsize >= kMppiObsTile && h->obs_ysize >= kMppiObsTile && h->obs_ysize % 4 == 0) {
+    const int ci = (int)std::floor((x - h->obs_xmin) / h->obs_res), cj = (int)std::floor((y - h->obs_ymin) / h->obs_res);
+    a.obs_ti0 = std::min(std::max(ci - kMppiObsTile / 2, 0), h->obs_xsize - kMppiObsTile);
+    a.obs_tj0 = std::min(std::max((cj - kMppiObsTile / 2) & ~3, 0), (h->obs_ysize - kMppiObsTile) & ~3);
+  }
+  // J >= 0 (sums of squares with non-negative weights): the high words of J order like J
+  a.thr_on = 1;
+  for (int i = 0; i < 3; i++) if (!(p.Q[i] >= 0.0) || !(p.P1[i] >= 0.0)) a.thr_on = 0;
+  if (!(p.R[0] >= 0.0) || !(p.R[1] >= 0.0) || (h->obs_on && (!(h->obs_weight >= 0.0) || !(h->obs_off >= 0.0)))) a.thr_on = 0;
   a.u_plan = h->d_u[h->cur];
   a.ext = h->d_ext; a.J_out = h->d_J; a.du_out = h->d_du; a.partials = h->d_partials;
+  a.tail = 0;
+  a.n_roll = h->grid;
   return a;
 }
 
-// the FAST variant needs: own noise, no taps, no obstacle term, a full last lane, TMA stores, and every half-step
-// heading increment inside the short Taylor range of mppi_sincos_small (1/16): |h w / 2| <= c_w (|uL| + |uR|) / 2 with
-// |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
-bool fast_variant(const b2n_mppi *h, const MppiArgs &a)
+// the fused tail's arguments: merge tree, update, and (sharded over peer memory) the exchange
+void arm_tail(b2n_mppi *h, MppiArgs &a)
+{
+  const b2n_mppi_params &p = h->p;
+  a.tail = 1;
+  a.plan_need = (unsigned long long)h->T * h->fused_calls;      // every step of every earlier fused call
+  h->fused_calls++;
+  a.arrive = h->d_sync; a.arrive_need = (unsigned long long)h->grid * h->fused_calls;
+  a.plan_seq = h->d_sync + 1;
+  a.k_total = (double)(p.rollouts_total > 0 ? p.rollouts_total : p.rollouts);
+  a.umax = p.max_wheel_vel;
+  a.uinit[0] = h->uinit[0]; a.uinit[1] = h->uinit[1];
+  a.u_next = h->d_u[h->cur ^ 1];
+  a.out = h->d_out_host;               // mapped pinned memory: the controls land on the host without a copy operation
+  a.out_seq = reinterpret_cast<unsigned long long *>(h->d_out_host + 2);
+  a.dbg = h->d_dbg;
+  a.seq = ++h->out_seq;
+  a.stepstats = h->d_stepstats;
+  a.merged = h->d_merged;
+  a.rank = 0; a.nranks = 1;
+  if (h->nranks > 1 && h->p2p_ready) {
+    for (int r = 0; r < h->nranks; r++) a.peer[r] = static_cast<unsigned long long *>(h->peer_base[r]);
+    a.rank = h->rank; a.nranks = h->nranks;
+    h->xchg_call++;
+    a.parity = (int)(h->xchg_call & 1ull);
+    a.call_id = (uint32_t)(h->xchg_call % 0xFFFFFFFFull) + 1u;
+  }
+}
+
+// the variates of call `call` into buffer `slot` (no-op when it already holds them)
+int ensure_noise(b2n_mppi *h, uint32_t call, int slot, bool pdl)
+{
+  if (h->z_call[slot] == (long long)call && h->z_seed[slot] == h->seed) return B2N_OK;
+  const size_t n = (size_t)h->K * (h->T / 2);
+  B2N_REQUIRE(h->d_z[slot], B2N_ERR_CUDA, "no buffer for the variates (the horizon does not fit a production shape)");
+  MppiNoiseArgs na;
+  std::memset(&na, 0, sizeof(na));
+  na.zbuf = h->d_z[slot]; na.K = h->K; na.half_T = h->T / 2; na.k_offset = h->p.rollout_offset; na.call = call;
+  for (int r = 0; r < 10; r++) {
+    na.key0[r] = (uint32_t)h->seed + (uint32_t)r * 0x9E3779B9u;
+    na.key1[r] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  const unsigned want = (unsigned)((n + 255) / 256);
+  cfg.gridDim = dim3(std::max(1u, std::min(want, (unsigned)h->n_sm * 8u))); cfg.blockDim = dim3(256); cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl && h->use_pdl) ? 1 : 0;
+  B2N_CUDA(cudaLaunchKernelEx(&cfg, mppi_noise_kernel, na));
+  h->launches++;
+  h->z_call[slot] = (long long)call; h->z_seed[slot] = h->seed;
+  return B2N_OK;
+}
+
+// 0 generic, 1 FAST, 2 FAST + obstacle term.  The FAST variants need: own noise, no taps, a full last lane, TMA stores, and
+// every half-step heading increment inside the short Taylor range of mppi_sincos_small (1/16): |h w / 2| <= c_w (|uL| + |uR|) / 2
+// with |u| <= max|plan| + 5.78 sigma (the binary32 Box-Muller cannot exceed sqrt(48 ln 2) = 5.77 standard deviations)
+int pick_variant(const b2n_mppi *h, const MppiArgs &a)
 {
   const double u_bound = 2.0 * h->plan_abs_max + 5.78 * (a.sigL + a.sigR);
-  return !a.external_noise && !a.capture && !a.obs_on && a.tma_store && h->T == h->S * h->G &&
-         0.5 * std::fabs(a.c_w) * u_bound <= 0.0625 && !h->force_generic;
+  const bool fast = !a.external_noise && !a.capture && a.tma_store && h->T == h->S * h->G &&
+                    0.5 * std::fabs(a.c_w) * u_bound <= 0.0625 && !h->force_generic;
+  return fast ? (a.obs_on ? 2 : 1) : 0;
 }
 
 // update kernel behind the rollout kernel with programmatic dependent launch: its CTAs may be scheduled while the
@@ -228,6 +321,16 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
   h->last_slot = h->ring_pos;
   a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
   h->ring_pos = (h->ring_pos + 1) % h->ring;
+  const int variant = pick_variant(h, a);
+  h->last_fast = variant != 0;
+  const bool ahead = variant != 0;
+  if (ahead) {
+    // normally a no-op: the variates were drawn behind the previous call
+    if (int rc = ensure_noise(h, h->call, (int)(h->call & 1u), false)) return rc;
+    a.zbuf = h->d_z[h->call & 1u];
+  }
+  const bool nccl_transport = h->nranks > 1 && !h->p2p_ready;
+  if (!nccl_transport) arm_tail(h, a);      // the whole call is this one launch
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->ev_used + 2 <= h->ev.size()) {
@@ -235,69 +338,45 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta)
     h->ev_used += 2;
     B2N_CUDA(cudaEventRecord(e0, h->stream));
   }
-  launch_rollout(h, a, fast_variant(h, a));
+  launch_rollout(h, a, variant);
   B2N_CUDA(cudaGetLastError());
   if (e1) B2N_CUDA(cudaEventRecord(e1, h->stream));
   h->launches++;
 
-  MppiUpdateArgs u;
-  std::memset(&u, 0, sizeof(u));
-  u.T = h->T;
-  u.inv_lambda = a.inv_lambda;
-  u.k_total = (double)(p.rollouts_total > 0 ? p.rollouts_total : p.rollouts);
-  u.umax = p.max_wheel_vel;
-  u.uinit[0] = h->uinit[0]; u.uinit[1] = h->uinit[1];
-  u.u_cur = h->d_u[h->cur];
-  u.u_next = h->d_u[h->cur ^ 1];
-  u.out = h->d_out_host;               // mapped pinned memory: the controls land on the host without a copy operation
-  u.out_seq = reinterpret_cast<unsigned long long *>(h->d_out_host + 2);
-  u.seq = ++h->out_seq;
-  u.stepstats = h->d_stepstats;
-  u.merged = h->d_merged;
-  if (h->nranks > 1 && h->p2p_ready) {
-    // merge + exchange over NVLink peer memory + update in one kernel (mppi_exchange_update_kernel)
-    u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 0;
-    MppiXchgArgs xa;
-    std::memset(&xa, 0, sizeof(xa));
-    for (int r = 0; r < h->nranks; r++) xa.peer[r] = static_cast<unsigned long long *>(h->peer_base[r]);
-    xa.rank = h->rank; xa.nranks = h->nranks;
-    h->xchg_call++;
-    xa.parity = (int)(h->xchg_call & 1ull);
-    xa.call_id = (uint32_t)(h->xchg_call % 0xFFFFFFFFull) + 1u;
-    {
-      cudaLaunchConfig_t cfg;
-      std::memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)h->T); cfg.blockDim = dim3(kMppiUpdateThreads); cfg.stream = h->stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
-      B2N_CUDA(cudaLaunchKernelEx(&cfg, mppi_exchange_update_kernel, u, xa));
-    }
-    B2N_CUDA(cudaGetLastError());
-    h->launches++;
-    h->cur ^= 1;
-    h->call++;
-    h->ext_armed = false;
-    h->pending = true;
-    return B2N_OK;
-  }
-  if (h->nranks > 1) {
-    // local merge -> one allgather of [T][6] doubles -> identical update on every rank
+  if (nccl_transport) {
+    // baseline transport of a sharded job: local merge -> one allgather of [T][6] doubles -> identical update on every
+    // rank, three more launches per call
+    MppiUpdateArgs u;
+    std::memset(&u, 0, sizeof(u));
+    u.T = h->T;
+    u.inv_lambda = a.inv_lambda;
+    u.k_total = (double)(p.rollouts_total > 0 ? p.rollouts_total : p.rollouts);
+    u.umax = p.max_wheel_vel;
+    u.uinit[0] = h->uinit[0]; u.uinit[1] = h->uinit[1];
+    u.u_cur = h->d_u[h->cur];
+    u.u_next = h->d_u[h->cur ^ 1];
+    u.out = h->d_out_host;
+    u.out_seq = reinterpret_cast<unsigned long long *>(h->d_out_host + 2);
+    u.seq = ++h->out_seq;
+    u.stepstats = h->d_stepstats;
+    u.merged = h->d_merged;
     u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 1;
     if (int rc = launch_update(h, u)) return rc;
     ncclResult_t r = ncclAllGather(h->d_merged, h->d_gathered, (size_t)h->T * 6, ncclDouble, h->comm, h->stream);
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
     u.partials = h->d_gathered; u.n_partials = h->nranks; u.p_stride = 6 * h->T; u.t_stride = 6; u.merge_only = 0;
-  } else {
-    u.partials = h->d_partials; u.n_partials = h->grid; u.p_stride = 6; u.t_stride = 6 * h->grid; u.merge_only = 0;
+    if (int rc = launch_update(h, u)) return rc;
   }
-  if (int rc = launch_update(h, u)) return rc;
 
   h->cur ^= 1;
   h->call++;
   h->ext_armed = false;
   h->pending = true;
+  // the next call's variates, behind this call: off the next call's critical path
+  if (ahead && h->noise_ahead) {
+    // (behind a fused call only: that call's successor finds the plan through its sequence word, not through this grid)
+    if (int rc = ensure_noise(h, h->call, (int)(h->call & 1u), !nccl_transport)) return rc;
+  }
   return B2N_OK;
 }
 
@@ -366,12 +445,27 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_TRY(cudaMemsetAsync(h->d_u[1], 0, 2 * T * sizeof(double), h->stream));
   B2N_TRY(cudaMalloc(&h->d_states, KT * 3 * sizeof(float)));
   B2N_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * T * 6 * sizeof(double)));
+  if (T == h->S * h->G) {
+    // the production variants read their variates from these (allocated here, never inside a call: an allocation can
+    // synchronise the device, and a sharded call in flight waits for ranks that this thread has not launched yet)
+    B2N_TRY(cudaMalloc(&h->d_z[0], KT / 2 * sizeof(float4)));
+    B2N_TRY(cudaMalloc(&h->d_z[1], KT / 2 * sizeof(float4)));
+  }
+  B2N_TRY(cudaMalloc(&h->d_sync, 2 * sizeof(unsigned long long)));
+  B2N_TRY(cudaMemsetAsync(h->d_sync, 0, 2 * sizeof(unsigned long long), h->stream));
+  if (const char *env = std::getenv("B2N_MPPI_DEBUG_TIMES")) {
+    if (env[0] == '1') {
+      B2N_TRY(cudaMalloc(&h->d_dbg, (size_t)(h->grid + T) * kMppiDbgSlots * sizeof(unsigned long long)));
+      B2N_TRY(cudaMemsetAsync(h->d_dbg, 0, (size_t)(h->grid + T) * kMppiDbgSlots * sizeof(unsigned long long), h->stream));
+    }
+  }
   B2N_TRY(cudaMalloc(&h->d_merged, (size_t)T * 6 * sizeof(double)));
   B2N_TRY(cudaMalloc(&h->d_stepstats, (size_t)T * 2 * sizeof(double)));
   B2N_TRY(cudaHostAlloc(&h->h_out, 4 * sizeof(double), cudaHostAllocMapped));
   std::memset(h->h_out, 0, 4 * sizeof(double));
   B2N_TRY(cudaHostGetDevicePointer(&h->d_out_host, h->h_out, 0));
   if (const char *env = std::getenv("B2N_MPPI_PDL")) h->use_pdl = env[0] != '0';
+  if (const char *env = std::getenv("B2N_MPPI_NOISE_AHEAD")) h->noise_ahead = env[0] != '0';
   B2N_TRY(cudaStreamSynchronize(h->stream));
 #undef B2N_TRY
   *out = h;
@@ -385,11 +479,12 @@ void b2n_mppi_destroy(b2n_mppi *h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) ncclCommDestroy(h->comm);
   for (int r = 0; r < (int)h->peer_base.size(); r++)
-    if (h->peer_base[r] && h->peer_base[r] != h->xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (!h->p2p_local && h->peer_base[r] && h->peer_base[r] != h->xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
   cudaFree(h->xchg);
   for (auto e : h->ev) cudaEventDestroy(e);
   cudaFree(h->d_u[0]); cudaFree(h->d_u[1]); cudaFree(h->d_states); cudaFree(h->d_partials);
-  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_stepstats);
+  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_stepstats); cudaFree(h->d_sync); cudaFree(h->d_dbg);
+  cudaFree(h->d_z[0]); cudaFree(h->d_z[1]);
   cudaFree(h->d_ext); cudaFree(h->d_J); cudaFree(h->d_du); cudaFree(h->d_w); cudaFree(h->d_obs);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -430,25 +525,30 @@ int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur)
 {
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
   B2N_REQUIRE(h->pending, B2N_ERR_INVALID_ARGUMENT, "b2n_mppi_wait: nothing enqueued");
-  // the update kernel publishes the controls and then the call's sequence number in mapped pinned memory: poll that
-  // word (about a microsecond after the store) instead of a stream synchronisation; every so often make sure the
-  // stream has not failed
-  volatile unsigned long long *seq = reinterpret_cast<volatile unsigned long long *>(h->h_out + 2);
+  // the kernel publishes the controls in mapped pinned memory as four 8-byte words, each carrying a 4-byte half of a control
+  // and the low half of the call's sequence number: poll until all four show this call's number (about a microsecond after
+  // the stores) instead of a stream synchronisation; every so often make sure the stream has not failed
+  volatile unsigned long long *w = reinterpret_cast<volatile unsigned long long *>(h->h_out);
+  const unsigned long long tag = h->out_seq & 0xFFFFFFFFull;
   const auto t_start = std::chrono::steady_clock::now();
-  for (unsigned spins = 0; *seq != h->out_seq; spins++) {
+  unsigned long long v[4];
+  for (unsigned spins = 0;; spins++) {
+    v[0] = w[0]; v[1] = w[1]; v[2] = w[2]; v[3] = w[3];
+    if ((v[0] >> 32) == tag && (v[1] >> 32) == tag && (v[2] >> 32) == tag && (v[3] >> 32) == tag) break;
     if ((spins & 0xFFFFu) == 0xFFFFu) {
       const cudaError_t e = cudaStreamQuery(h->stream);
-      if (e == cudaSuccess) break;                  // finished: the word is visible by now
-      if (e != cudaErrorNotReady) { set_error("stream failed while waiting for the controls: %s", cudaGetErrorString(e)); return B2N_ERR_CUDA; }
+      if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("stream failed while waiting for the controls: %s", cudaGetErrorString(e)); return B2N_ERR_CUDA; }
       if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(60)) {
         set_error("no controls after 60 s (a sharded job waits for every rank: is one of them gone?)");
         return B2N_ERR_COMM;
       }
     }
   }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  if (ul) *ul = h->h_out[0];
-  if (ur) *ur = h->h_out[1];
+  const unsigned long long bl = (v[0] & 0xFFFFFFFFull) | (v[1] << 32), br = (v[2] & 0xFFFFFFFFull) | (v[3] << 32);
+  double dl, dr;
+  std::memcpy(&dl, &bl, 8); std::memcpy(&dr, &br, 8);
+  if (ul) *ul = dl;
+  if (ur) *ur = dr;
   return B2N_OK;
 }
 
@@ -580,6 +680,8 @@ int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int y
   if (int rc = set_device(h)) return rc;
   if (!dist) { h->obs_on = 0; return B2N_OK; }
   B2N_REQUIRE(xsize > 0 && ysize > 0 && resolution > 0.0, B2N_ERR_INVALID_ARGUMENT, "bad obstacle field geometry");
+  // the reference's cell index is i * xsize + j with i < xsize, j < ysize (grid_mapper.cpp:890-898): square grids only, as b2n_pf_create
+  B2N_REQUIRE(xsize == ysize, B2N_ERR_UNSUPPORTED, "obstacle field must be square (got %d x %d)", xsize, ysize);
   cudaFree(h->d_obs); h->d_obs = nullptr;
   const size_t n = (size_t)xsize * ysize;
   B2N_CUDA(cudaMalloc(&h->d_obs, n * sizeof(float)));
@@ -595,6 +697,7 @@ int b2n_mppi_obstacle_field_device(b2n_mppi *h, int xsize, int ysize, double xmi
 {
   B2N_REQUIRE(h && device_field, B2N_ERR_INVALID_ARGUMENT, "null argument");
   B2N_REQUIRE(xsize > 0 && ysize > 0 && resolution > 0.0, B2N_ERR_INVALID_ARGUMENT, "bad obstacle field geometry");
+  B2N_REQUIRE(xsize == ysize, B2N_ERR_UNSUPPORTED, "obstacle field must be square (got %d x %d)", xsize, ysize);
   if (int rc = set_device(h)) return rc;
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   const size_t n = (size_t)xsize * ysize;
@@ -626,6 +729,47 @@ int b2n_mppi_set_state_ring(b2n_mppi *h, int n)
   B2N_CUDA(cudaMalloc(&fresh, (size_t)n * h->K * h->T * 3 * sizeof(float)));
   cudaFree(h->d_states);
   h->d_states = fresh; h->ring = n; h->ring_pos = 0; h->last_slot = 0;
+  return B2N_OK;
+}
+
+namespace
+{
+__global__ void box_muller_range_kernel(uint32_t first, uint32_t count, uint32_t rb, float2 *z)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    float2 o;
+    box_muller_f32((first + i) << 9, rb, o.x, o.y);
+    z[i] = o;
+  }
+}
+} // namespace
+
+int b2n_test_box_muller(uint32_t first, uint32_t count, uint32_t rb, float *z)
+{
+  B2N_REQUIRE(z && count > 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
+  float2 *d = nullptr;
+  B2N_CUDA(cudaMalloc(&d, (size_t)count * sizeof(float2)));
+  box_muller_range_kernel<<<1184, 256>>>(first, count, rb, d);
+  cudaError_t e = cudaMemcpy(z, d, (size_t)count * sizeof(float2), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  B2N_CUDA(e);
+  return B2N_OK;
+}
+
+int b2n_mppi_debug_times(b2n_mppi *h, unsigned long long *out, size_t count, int *grid)
+{
+  B2N_REQUIRE(h && out && grid, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->d_dbg, B2N_ERR_INVALID_ARGUMENT, "set B2N_MPPI_DEBUG_TIMES=1 before creating the handle");
+  const size_t n = (size_t)(h->grid + h->T) * kMppiDbgSlots;
+  B2N_REQUIRE(count >= n, B2N_ERR_INVALID_ARGUMENT, "need (grid + T) * %d = %zu words", kMppiDbgSlots, n);
+  *grid = h->grid;
+  return copy_out(h, out, h->d_dbg, n * sizeof(unsigned long long));
+}
+
+int b2n_mppi_last_variant(const b2n_mppi *h, int *fast)
+{
+  B2N_REQUIRE(h && fast, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  *fast = h->last_fast;
   return B2N_OK;
 }
 
@@ -672,7 +816,12 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
   B2N_REQUIRE(h && avg_ms && launches > 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
   if (int rc = set_device(h)) return rc;
   MppiArgs a = make_args(h, x, y, theta);
-  const bool fast = fast_variant(h, a);
+  const int variant = pick_variant(h, a);      // a.tail = 0: the rollout phase and the CTA partials only
+  if (variant != 0) {
+    if (int rc = ensure_noise(h, h->call, (int)(h->call & 1u), false)) return rc;
+    a.zbuf = h->d_z[h->call & 1u];
+  }
+  a.plan_seq = h->d_sync + 1; a.plan_need = (unsigned long long)h->T * h->fused_calls;
   cudaEvent_t e0, e1;
   B2N_CUDA(cudaEventCreate(&e0));
   B2N_CUDA(cudaEventCreate(&e1));
@@ -681,7 +830,7 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
     a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
     h->ring_pos = (h->ring_pos + 1) % h->ring;
     a.call = h->call + (uint32_t)i;
-    launch_rollout(h, a, fast);
+    launch_rollout(h, a, variant);
   }
   B2N_CUDA(cudaGetLastError());
   B2N_CUDA(cudaEventRecord(e1, h->stream));
@@ -730,6 +879,26 @@ int b2n_mppi_p2p_init(b2n_mppi *h, int rank, int nranks, const void *handles)
       return B2N_ERR_COMM;
     }
   }
+  h->rank = rank; h->nranks = nranks; h->p2p_ready = true; h->xchg_call = 0;
+  return B2N_OK;
+}
+
+int b2n_mppi_p2p_area(b2n_mppi *h, void **area)
+{
+  B2N_REQUIRE(h && area, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->xchg, B2N_ERR_INVALID_ARGUMENT, "b2n_mppi_p2p_export must come first");
+  *area = h->xchg;
+  return B2N_OK;
+}
+
+int b2n_mppi_p2p_init_local(b2n_mppi *h, int rank, int nranks, void *const *areas)
+{
+  B2N_REQUIRE(h && areas, B2N_ERR_INVALID_ARGUMENT, "null argument");
+  B2N_REQUIRE(h->xchg && nranks == h->xchg_nranks && rank >= 0 && rank < nranks, B2N_ERR_INVALID_ARGUMENT,
+              "b2n_mppi_p2p_export(h, %d, ...) must come first on every rank", nranks);
+  B2N_REQUIRE(areas[rank] == h->xchg, B2N_ERR_INVALID_ARGUMENT, "areas[rank] must be this handle's own area");
+  h->peer_base.assign(areas, areas + nranks);
+  h->p2p_local = true;
   h->rank = rank; h->nranks = nranks; h->p2p_ready = true; h->xchg_call = 0;
   return B2N_OK;
 }

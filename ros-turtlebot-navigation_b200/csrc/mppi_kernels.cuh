@@ -1,4 +1,4 @@
-// mppi_kernels.cuh - the MPPI hot loop of controller::MPPI::newControls() as sm_100a kernels.
+// mppi_kernels.cuh - the MPPI hot loop of controller::MPPI::newControls() as ONE sm_100a kernel per call.
 //
 // Reference path (all under /root/reference): controller/src/controller/mppi.cpp:72-140 (K rollouts,
 // loss matrix, cost-to-go, T softmaxes over K, clamp, shift), :173-184 (perturbations),
@@ -19,11 +19,18 @@
 //   * the only mandatory HBM traffic is the fp32 [K][T][3] state tensor: each warp stages its rows in
 //     shared memory and one lane hands them to the TMA unit (cp.async.bulk shared->global), double
 //     buffered so the next rollouts' math overlaps the store.
-//   * the T softmaxes are carried ONLINE: every lane keeps (min J, sum e, sum e*duL, sum e*duR,
-//     sum duL, sum duR) for its S steps across all rollouts it sees, lane groups and warps merge at the
-//     end, each CTA writes one [T][6] partial.  J never makes a round trip through HBM.
-//   * mppi_update_kernel merges the partials (from all CTAs, or from all ranks after the allgather),
-//     applies the weighted update, clamps, emits the first control and shifts the plan.
+//   * the T softmaxes are carried ONLINE: every lane keeps (min J, sum e, sum e*duL, sum e*duR) for its S steps in
+//     shared memory and only touches them when a rollout's cost-to-go comes within the exponent range of the lane's
+//     running minimum (a one-instruction integer test on the high word against a threshold held in a register);
+//     sum duL, sum duR live in registers.  J never makes a round trip through HBM.
+//   * THE CALL IS ONE LAUNCH.  The grid is the rollout CTAs followed by T MERGER CTAs.  Every rollout CTA merges its warps
+//     into one [T][6] partial and counts itself in (a release reduction, nothing to wait for).  The merger CTAs carry the
+//     highest block indices, so they take the SM slots the first rollout CTAs leave; merger t waits for the count, merges
+//     step t's partials of all CTAs (minimum first, every partial rescaled once, fixed order: bit-reproducible), exchanges
+//     the result with the other ranks over NVLink peer memory when the job is sharded, applies the update of
+//     mppi.cpp:112-137 and publishes the first control in mapped pinned host memory.  (A two-level "last arriver merges"
+//     tree inside the rollout CTAs was built first and measured 3x slower: two fence + atomic + dependent-load rounds in
+//     series on ONE CTA against T CTAs working side by side.)
 #pragma once
 
 #include "common.cuh"
@@ -31,9 +38,9 @@
 namespace b2n
 {
 
-constexpr int kMppiThreads = 256;            // 8 warps per CTA
-constexpr int kMppiWarps = kMppiThreads / 32;
 constexpr int kMppiMaxT = 256;               // 32 lanes x 8 steps
+constexpr int kMppiMaxRanks = 64;
+constexpr int kMppiXchgWords = 12;           // 6 doubles = 12 payload halves
 
 struct MppiArgs
 {
@@ -41,22 +48,50 @@ struct MppiArgs
   double c_v, c_w;            // (r/2)(h/6) and (r/L) h: position and heading increment factors (mppi.hpp:45-47, rk4.cpp:114)
   double Q[3], R[2], P1[3];
   double inv_lambda, sigL, sigR;
+  double cut_lambda;          // a rollout whose cost-to-go exceeds the running minimum by more than this has weight 0 in fp64
   double x0[3], xd[3];
   double cos0, sin0;          // of the start heading x0[2], from the host's libm
+  // polynomial coefficients, passed as parameters so that DFMA takes them from the constant bank (as immediates every
+  // use costs two uniform-register moves): sin / cos Taylor terms
+  double ks3, ks5, ks7, ks9, kc2, kc4, kc6, kc8, kc10;
   int T, K, k_offset;
-  uint32_t seed_lo, seed_hi, call;
+  int thr_on;                 // every cost weight is >= 0, so J >= 0 and the high words of J order like J (threshold test below)
+  uint32_t call;
+  uint32_t key0[10], key1[10];   // Philox round keys: seed lo / hi + round * Weyl constants
   int external_noise, capture, tma_store;
   // optional obstacle term (extension, see b2nav.h)
   int obs_on, obs_xsize, obs_ysize;
   double obs_xmin, obs_ymin, obs_xmax, obs_ymax, obs_res, obs_weight, obs_d0, obs_off;
   const float *obs_dist;
+  int obs_ti0, obs_tj0;       // first cell of the tile staged in shared memory (kMppiObsTile square), -1: no tile
   // buffers
   const double *u_plan;    // [2][T]
   float *states;           // [K][T][3]
   const double *ext;       // [K][T][2] or null
+  const float4 *zbuf;      // [K][T/2] the call's standard normals (zL_t, zR_t, zL_t+1, zR_t+1), drawn ahead by mppi_noise_kernel (FAST variants)
   double *J_out;           // [K][T] (capture)
   double *du_out;          // [K][T][2] (capture)
   double *partials;        // [T][gridDim.x][6]: a step's partials of all CTAs are contiguous for the CTA that merges them
+  // ---- fused tail: merge tree, exchange, update (mppi.cpp:112-137) ----
+  int tail;                // 0: stop after the CTA partials (NCCL transport, bench hook b2n_mppi_time_rollout)
+  int n_roll;              // rollout CTAs (block indices below this); with tail: gridDim.x = n_roll + T, the rest are mergers
+  unsigned long long *arrive;        // rollout CTAs that have published their partial, all fused calls of the handle together
+  unsigned long long arrive_need;    //   its value when this call's are all in: n_roll x (number of fused calls so far)
+  double k_total, umax;
+  double uinit[2];
+  double *u_next;          // [2][T]
+  double *out;             // [2] first control of the updated plan (mapped pinned host memory)
+  unsigned long long *out_seq;   // completion word next to it: set to `seq` after the controls are visible to the host
+  unsigned long long seq;
+  double *stepstats;       // [T][2] (min J, sum w) for the weights tap
+  double *merged;          // [T][6] this rank's merged sums (tap)
+  unsigned long long *dbg;       // [grid][8] stage timestamps (globaltimer ns) of every CTA's thread 0, tuning runs only (null: off)
+  unsigned long long *plan_seq;  // steps whose update is complete, all fused calls of the handle together (device memory):
+  unsigned long long plan_need;  //   the value the CTAs of this call wait for before they read the plan (T per earlier call)
+  // sharded job: peer-memory exchange areas [2 parities][nranks][T][12 words], see mppi_exchange()
+  int rank, nranks, parity;
+  uint32_t call_id;
+  unsigned long long *peer[kMppiMaxRanks];
 };
 
 struct MppiUpdateArgs
@@ -75,262 +110,826 @@ struct MppiUpdateArgs
   double *merged;          // [T][6] when merge_only
 };
 
-__device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, double x, double y)
+constexpr int kMppiObsTile = 32;             // cells per side of the obstacle-field tile staged through TMA
+
+// the obstacle term of one state (extension, b2nav.h): the distance comes from the tile in shared memory when the cell
+// is inside it (every state of a horizon lies within a few cells of the start pose), from global memory otherwise
+__device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, const float *tile, double x, double y)
 {
   if (!(x >= a.obs_xmin && x <= a.obs_xmax) || !(y >= a.obs_ymin && y <= a.obs_ymax)) return a.obs_off;
   double i = floor((x - a.obs_xmin) / a.obs_res);
   if (i == (double)a.obs_xsize) i -= 1.0;
   double j = floor((y - a.obs_ymin) / a.obs_res);
   if (j == (double)a.obs_ysize) j -= 1.0;
-  const double d = (double)__ldg(&a.obs_dist[(int)i * a.obs_xsize + (int)j]);
-  const double pen = a.obs_d0 - d;
+  const int ii = (int)i, jj = (int)j;
+  const unsigned ti = (unsigned)(ii - a.obs_ti0), tj = (unsigned)(jj - a.obs_tj0);
+  float df;
+  if (a.obs_ti0 >= 0 && ti < (unsigned)kMppiObsTile && tj < (unsigned)kMppiObsTile) df = tile[ti * kMppiObsTile + tj];
+  else df = __ldg(&a.obs_dist[(size_t)ii * a.obs_ysize + jj]);       // row-major [xsize][ysize]
+  const double pen = a.obs_d0 - (double)df;
   return pen > 0.0 ? a.obs_weight * pen * pen : 0.0;
 }
 
-// exp(x) for x <= 0.  Below -708 the result is subnormal or zero: added to a softmax sum that already holds the
-// minimum's 1.0 it cannot change a bit, so the evaluation is skipped (at the shipped lambda = 0.01 that is almost
-// every term).
-__device__ __forceinline__ double mppi_exp_neg(double x) { return x > -708.0 ? exp(x) : 0.0; }
+// exp(x) for x <= 0.  Below the cut the result cannot change a softmax sum that already holds the minimum's 1.0, so
+// the evaluation is skipped (at the shipped lambda = 0.01 that is almost every term).
+//   exact (generic kernel variant, update kernels): libdevice exp, cut at -708 (subnormal results dropped).
+//   fast  (production variant): 2^x split into an integer and a fraction in [-1/2, 1/2]; the fraction goes through the
+//          SFU (ex2.approx.f32, relative error 2^-22), the integer into the exponent field.  2.5e-7 relative on a softmax
+//          term, against the 1e-5 the contract allows on weights and controls; cut at -700 so the exponent never
+//          reaches the subnormal range.
+template <bool FASTEXP>
+__device__ __forceinline__ double mppi_exp_neg(double x)
+{
+  if (!FASTEXP) return x > -708.0 ? exp(x) : 0.0;
+  if (!(x > -700.0)) return 0.0;
+  const double t = x * 1.4426950408889634;                 // log2(e)
+  const double tn = t + 6755399441055744.0;                // 1.5 * 2^52: the low word now holds rint(t)
+  const int n = __double2loint(tn);
+  const float f = (float)(t - (tn - 6755399441055744.0));  // in [-1/2, 1/2]
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
+  const double pd = (double)p;                             // in [0.707, 1.415]
+  return __hiloint2double(__double2hiint(pd) + (n << 20), __double2loint(pd));
+}
 
 // sin and cos of a small angle by Taylor series.  Generic: |d| <= 1/8 with terms to d^9 / d^10 (truncation < 3e-16
 // relative), full range falls back to sincos.  ALWAYS_SMALL (the host has proved |d| <= 1/16): terms to d^7 / d^6,
 // truncation 4e-17 / 6e-15 absolute.
 template <bool ALWAYS_SMALL>
-__device__ __forceinline__ void mppi_sincos_small(double d, double &sn, double &cs)
+__device__ __forceinline__ void mppi_sincos_small(const MppiArgs &a, double d, double &sn, double &cs)
 {
   const double z = d * d;
   if (ALWAYS_SMALL) {
-    double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);    // -1/7!, 1/5!
-    ps = fma(z, ps, -1.6666666666666666e-01);                               // -1/3!
+    double ps = fma(z, a.ks7, a.ks5);    // -1/7!, 1/5!
+    ps = fma(z, ps, a.ks3);              // -1/3!
     sn = fma(d * z, ps, d);
-    double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);    // -1/6!, 1/4!
-    pc = fma(z, pc, -0.5);
+    double pc = fma(z, a.kc6, a.kc4);    // -1/6!, 1/4!
+    pc = fma(z, pc, a.kc2);              // -1/2
     cs = fma(z, pc, 1.0);
     return;
   }
   if (fabs(d) > 0.125) { sincos(d, &sn, &cs); return; }
-  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
-  ps = fma(z, ps, 8.3333333333333332e-03);                                // 1/5!
-  ps = fma(z, ps, -1.6666666666666666e-01);                               // -1/3!
+  double ps = fma(z, a.ks9, a.ks7);      // 1/9!, -1/7!
+  ps = fma(z, ps, a.ks5);
+  ps = fma(z, ps, a.ks3);
   sn = fma(d * z, ps, d);
-  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);    // -1/10!, 1/8!
-  pc = fma(z, pc, -1.3888888888888889e-03);                               // -1/6!
-  pc = fma(z, pc, 4.1666666666666664e-02);                                // 1/4!
-  pc = fma(z, pc, -0.5);
+  double pc = fma(z, a.kc10, a.kc8);     // -1/10!, 1/8!
+  pc = fma(z, pc, a.kc6);
+  pc = fma(z, pc, a.kc4);
+  pc = fma(z, pc, a.kc2);
   cs = fma(z, pc, 1.0);
 }
 
-// dynamic shared memory: [warps][2][32*S*3] fp32 staging rows, then [S*6][threads] fp64 online-softmax accumulators
-// (kept out of the register file so that three CTAs fit an SM; reused as [warps][G*S][6] for the CTA merge)
-// (7-warp CTAs stage through ONE buffer so that four of them fit an SM)
-__host__ __device__ constexpr int mppi_stage_buffers(int NW) { return NW == 7 ? 1 : 2; }
-__host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW)
+// ---- segmented warp scans over the G lanes of a rollout -----------------------------------------------------------
+// shfl.sync returns, next to the value, whether the source lane was inside the segment; the dependent arithmetic is
+// predicated on it directly (the C++ intrinsics drop that predicate, and `if (g >= d)` costs a compare plus two
+// selects per double).
+template <int G>
+__device__ __forceinline__ void scan_rot_up(double &tc, double &ts, double &tth, int d)
 {
-  return (size_t)NW * mppi_stage_buffers(NW) * 32 * S * 3 * sizeof(float) + (size_t)S * 6 * NW * 32 * sizeof(double);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 a0, a1, b0, b1, c0, c1;\n\t"
+      ".reg .f64 oc, os, ot, m0, m1;\n\t"
+      "mov.b64 {a0, a1}, %0;\n\t"
+      "mov.b64 {b0, b1}, %1;\n\t"
+      "mov.b64 {c0, c1}, %2;\n\t"
+      "shfl.sync.up.b32 a0|p, a0, %3, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 a1, a1, %3, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 b0, b0, %3, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 b1, b1, %3, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 c0, c0, %3, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 c1, c1, %3, %4, 0xffffffff;\n\t"
+      "mov.b64 oc, {a0, a1};\n\t"
+      "mov.b64 os, {b0, b1};\n\t"
+      "mov.b64 ot, {c0, c1};\n\t"
+      "@p mul.f64 m0, %1, os;\n\t"            // ts * os
+      "@p mul.f64 m1, %1, oc;\n\t"            // ts * oc
+      "@p neg.f64 m0, m0;\n\t"
+      "@p fma.rn.f64 m0, %0, oc, m0;\n\t"     // tc * oc - ts * os
+      "@p fma.rn.f64 %1, %0, os, m1;\n\t"     // tc * os + ts * oc
+      "@p mov.f64 %0, m0;\n\t"
+      "@p add.f64 %2, %2, ot;\n\t"
+      "}"
+      : "+d"(tc), "+d"(ts), "+d"(tth)
+      : "r"(d), "n"((32 - G) << 8));
 }
 
-// FAST = the production configuration, decided on the host: own noise, no capture taps, no obstacle term, T == G * S
-// (no partially filled lanes), TMA row stores, and half-step heading increments provably inside the Taylor range.
-// NW = warps per CTA: 8, or 7 (four CTAs = 28 warps per SM) where that divides the job into equal passes.
-template <int S, int G, bool FAST, int NW>
-__global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 && NW != 7 ? 3 : 4))) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+template <int G>
+__device__ __forceinline__ void scan_add2_up(double &x, double &y, int d)
 {
-  constexpr int kMppiWarps = NW, kMppiThreads = NW * 32;     // shadow the defaults: every layout below follows the CTA shape
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 a0, a1, b0, b1;\n\t"
+      ".reg .f64 ox, oy;\n\t"
+      "mov.b64 {a0, a1}, %0;\n\t"
+      "mov.b64 {b0, b1}, %1;\n\t"
+      "shfl.sync.up.b32 a0|p, a0, %2, %3, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 a1, a1, %2, %3, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 b0, b0, %2, %3, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 b1, b1, %2, %3, 0xffffffff;\n\t"
+      "mov.b64 ox, {a0, a1};\n\t"
+      "mov.b64 oy, {b0, b1};\n\t"
+      "@p add.f64 %0, %0, ox;\n\t"
+      "@p add.f64 %1, %1, oy;\n\t"
+      "}"
+      : "+d"(x), "+d"(y)
+      : "r"(d), "n"((32 - G) << 8));
+}
+
+template <int G>
+__device__ __forceinline__ void scan_add_down(double &x, int d)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 a0, a1;\n\t"
+      ".reg .f64 ox;\n\t"
+      "mov.b64 {a0, a1}, %0;\n\t"
+      "shfl.sync.down.b32 a0|p, a0, %1, %2, 0xffffffff;\n\t"
+      "shfl.sync.down.b32 a1, a1, %1, %2, 0xffffffff;\n\t"
+      "mov.b64 ox, {a0, a1};\n\t"
+      "@p add.f64 %0, %0, ox;\n\t"
+      "}"
+      : "+d"(x)
+      : "r"(d), "n"(((32 - G) << 8) | 0x1f));
+}
+
+// value of the neighbouring lane inside the segment (delta 1), or `edge` at the segment boundary
+template <int G, bool UP>
+__device__ __forceinline__ double shift1(double v, double edge)
+{
+  double o;
+  if (UP)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 a0, a1;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "shfl.sync.up.b32 a0|p, a0, 1, %3, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 a1, a1, 1, %3, 0xffffffff;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "@!p mov.f64 %0, %2;\n\t"
+        "}"
+        : "=d"(o)
+        : "d"(v), "d"(edge), "n"((32 - G) << 8));
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 a0, a1;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "shfl.sync.down.b32 a0|p, a0, 1, %3, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 a1, a1, 1, %3, 0xffffffff;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "@!p mov.f64 %0, %2;\n\t"
+        "}"
+        : "=d"(o)
+        : "d"(v), "d"(edge), "n"(((32 - G) << 8) | 0x1f));
+  return o;
+}
+
+// ---- noise ----------------------------------------------------------------------------------------------------------
+// normal_quad_f32 of common.cuh with the Philox round keys taken from the kernel parameters (constant bank) instead of
+// being re-derived from the seed every pass
+__device__ __forceinline__ void mppi_normal_quad(const MppiArgs &a, uint32_t stream, uint32_t index, float z[4])
+{
+  uint32_t c0 = index, c1 = stream, c2 = a.call, c3 = kDomainMppi;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ a.key0[r], n2 = hi0 ^ c3 ^ a.key1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  box_muller_f32(c0, c1, z[0], z[1]);
+  box_muller_f32(c2, c3, z[2], z[3]);
+}
+
+constexpr int kMppiDbgSlots = 24;
+// SM clock of warp 0 at a point inside its first pass (slots 8 and up)
+__device__ __forceinline__ void mppi_clock(const MppiArgs &a, bool first, int j)
+{
+  if (a.dbg && first && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + j] = (unsigned long long)clock64();
+}
+
+__device__ __forceinline__ void mppi_stamp(const MppiArgs &a, int j)
+{
+  if (a.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + j] = t;
+  }
+}
+
+// ---- merge of n accumulator sets per time step by one CTA ----------------------------------------------------------------
+// Every set is (min J, sum e, sum e*duL, sum e*duR, sum duL, sum duR) with the three weighted sums relative to the set's
+// own minimum.  Thread x handles step t = x mod TP2 and the sets q, q + Q, q + 2Q, ... (q = x / TP2, Q = NT / TP2, TP2 =
+// the horizon rounded up to a power of two): minimum first, then every set rescaled ONCE (independent exponentials) and
+// summed in index order, then the Q partial results of a step summed in q order - a fixed order, whatever the arrival
+// order of the sets' producers.  `load(t, i, v)` fetches set i of step t, `load_min(t, i)` its minimum only.
+// scratch: NT * 6 doubles of shared memory.  The result is valid in threads x < T (t = x).
+template <int NT, bool FASTEXP, class LoadMin, class Load>
+__device__ __forceinline__ void mppi_merge_sets(int T, int TP2, int n, double inv_lambda, double *scratch, LoadMin load_min, Load load, double out[6])
+{
+  constexpr int kU = 4;       // sets fetched per round trip: their loads are issued together (an L2 round trip each otherwise)
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  const int x = threadIdx.x;
+  const int t = x & (TP2 - 1), q = x / TP2, Q = NT / TP2;
+  double *smin = scratch, *ssum = scratch + NT;           // [Q][TP2], [Q][TP2][5]
+  double m = inf;
+  if (t < T) {
+    for (int i0 = q; i0 < n; i0 += kU * Q) {
+      double mv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) mv[u] = (i0 + u * Q < n) ? load_min(t, i0 + u * Q) : inf;
+#pragma unroll
+      for (int u = 0; u < kU; u++) m = fmin(m, mv[u]);
+    }
+  }
+  smin[q * TP2 + t] = m;
+  __syncthreads();
+  m = smin[t];
+  for (int qq = 1; qq < Q; qq++) m = fmin(m, smin[qq * TP2 + t]);
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (t < T) {
+    for (int i0 = q; i0 < n; i0 += kU * Q) {
+      double v[kU][6];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (i0 + u * Q < n) load(t, i0 + u * Q, v[u]);
+        else { v[u][0] = inf; v[u][4] = 0.0; v[u][5] = 0.0; }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (v[u][0] != inf) {      // an empty set has min = +inf and zero sums
+          const double f = (v[u][0] == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - v[u][0]) * inv_lambda);
+          s[0] = fma(v[u][1], f, s[0]); s[1] = fma(v[u][2], f, s[1]); s[2] = fma(v[u][3], f, s[2]);
+        }
+        s[3] += v[u][4]; s[4] += v[u][5];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++) ssum[(q * TP2 + t) * 5 + j] = s[j];
+  __syncthreads();
+  out[0] = m;
+  if (q == 0) {
+    for (int qq = 1; qq < Q; qq++) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) s[j] += ssum[(qq * TP2 + t) * 5 + j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++) out[1 + j] = s[j];
+  __syncthreads();        // the scratch area may be reused by the next merge
+}
+
+// the control update of mppi.cpp:112-137 for step t from the fully merged sums (one thread)
+template <class A>
+__device__ __forceinline__ void mppi_apply_update(const A &a, const double *u_cur, int t, double m, double S, double Aw, double Bw, double DL, double DR)
+{
+  const int T = a.T;
+  // w_k = exp(-(J_k - min)/lambda) + 1e-8, normalised (mppi.cpp:117-118)
+  const double sumw = S + a.k_total * 1e-8;
+  const double inv = 1.0 / sumw;
+  double nl = u_cur[t] + (Aw + 1e-8 * DL) * inv;            // mppi.cpp:120-121
+  double nr = u_cur[T + t] + (Bw + 1e-8 * DR) * inv;
+  nl = fmin(fmax(nl, -a.umax), a.umax);                     // mppi.cpp:124-125
+  nr = fmin(fmax(nr, -a.umax), a.umax);
+  if (t == 0) {                                             // mppi.cpp:129-131
+    if (a.out_seq) {
+      // the host polls these words instead of paying a stream synchronisation for 16 bytes.  Four 8-byte words, each a
+      // 4-byte half of a control next to the low half of the call's sequence number: a word that shows the sequence number
+      // IS its payload, so nothing has to be ordered and no system-scope fence sits on the call's critical path
+      const unsigned long long tag = (a.seq & 0xFFFFFFFFull) << 32;
+      unsigned long long *w = reinterpret_cast<unsigned long long *>(a.out);
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w + 0), "l"(tag | (unsigned)__double2loint(nl)) : "memory");
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w + 1), "l"(tag | (unsigned)__double2hiint(nl)) : "memory");
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w + 2), "l"(tag | (unsigned)__double2loint(nr)) : "memory");
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w + 3), "l"(tag | (unsigned)__double2hiint(nr)) : "memory");
+    } else {
+      a.out[0] = nl; a.out[1] = nr;
+    }
+  }
+  else { a.u_next[t - 1] = nl; a.u_next[T + t - 1] = nr; }  // mppi.cpp:134
+  if (t == T - 1) { a.u_next[T - 1] = a.uinit[0]; a.u_next[2 * T - 1] = a.uinit[1]; }   // mppi.cpp:136-137
+  a.stepstats[2 * t] = m;
+  a.stepstats[2 * t + 1] = sumw;
+}
+
+// ---- sharded rollouts: the exchange over NVLink peer memory ---------------------------------------------
+// Every rank owns an exchange area [2 call parities][nranks][T][12] of 8-byte words; peer[j] is rank j's area mapped
+// into this process (CUDA IPC).  Merger CTA t sends this rank's merged sums of step t to every rank (its own included:
+// one code path) in the low-latency style of NCCL's LL protocol: each 8-byte word carries 4 bytes of payload and the
+// 32-bit call id, and 8-byte stores are single NVLink transactions, so a word whose upper half shows the current call id
+// IS its payload - no fence, no separate flag, one NVLink write latency.  The CTA then spins on the 12 x nranks words of
+// its own area, and thread 0 folds the nranks results in rank order (identical on every rank, so the plan stays replicated
+// without a broadcast).  No NCCL call, no extra launch.
+// A slot of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's
+// data of call c + 1, which was sent after this rank finished reading call c: two parities are enough.
+template <int NT, bool FASTEXP>
+__device__ __forceinline__ void mppi_exchange_step(const MppiArgs &a, int t, double &m, double &S, double &A, double &B, double &DL, double &DR)
+{
+  __shared__ uint32_t mine[kMppiXchgWords];
+  __shared__ uint32_t all[kMppiMaxRanks][kMppiXchgWords];
+  __shared__ double fac[kMppiMaxRanks];
+  const int T = a.T, par = a.parity;
+  if (threadIdx.x == 0) {
+    const double v[6] = {m, S, A, B, DL, DR};
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      mine[2 * i] = (uint32_t)__double2loint(v[i]);
+      mine[2 * i + 1] = (uint32_t)__double2hiint(v[i]);
+    }
+  }
+  __syncthreads();
+  const int n_words = a.nranks * kMppiXchgWords;
+  for (int i = threadIdx.x; i < n_words; i += NT) {
+    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
+    // word w of this rank's slot in rank r's area
+    unsigned long long *dst = a.peer[r] + (((size_t)par * a.nranks + a.rank) * T + t) * kMppiXchgWords + w;
+    const unsigned long long packed = ((unsigned long long)a.call_id << 32) | mine[w];
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(packed) : "memory");
+  }
+  for (int i = threadIdx.x; i < n_words; i += NT) {
+    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
+    const unsigned long long *src = a.peer[a.rank] + (((size_t)par * a.nranks + r) * T + t) * kMppiXchgWords + w;
+    unsigned long long got;
+    unsigned polls = 0;
+    do {
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+      if (++polls == (1u << 27)) __trap();          // about a minute without the peer's word: fail loudly, not silently
+    } while ((uint32_t)(got >> 32) != a.call_id);
+    all[r][w] = (uint32_t)got;
+  }
+  __syncthreads();
+  // fold the nranks results in rank order (identical on every rank).  The rescale factors are independent of one
+  // another: thread r computes rank r's (one exponential each, side by side), thread 0 then runs the ordered sums
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  auto val = [&](int r, int i) { return __hiloint2double((int)all[r][2 * i + 1], (int)all[r][2 * i]); };
+  m = inf;
+  for (int r = 0; r < a.nranks; r++) m = fmin(m, val(r, 0));
+  if ((int)threadIdx.x < a.nranks) {
+    const double mr = val((int)threadIdx.x, 0);
+    fac[threadIdx.x] = (mr == inf) ? 0.0 : (mr == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - mr) * a.inv_lambda);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  S = A = B = DL = DR = 0.0;
+  for (int r = 0; r < a.nranks; r++) {
+    if (val(r, 0) != inf) {
+      const double f = fac[r];
+      S = fma(val(r, 1), f, S); A = fma(val(r, 2), f, A); B = fma(val(r, 3), f, B);
+    }
+    DL += val(r, 4); DR += val(r, 5);
+  }
+}
+
+// merge of one step's partials by one CTA of NT threads: minimum first, then every partial rescaled once (independent
+// exponentials), plain sums in a fixed order.  partial p of step t at partials + p * p_stride + t * t_stride (doubles).
+// The result is valid in thread 0.
+template <int NT, bool FASTEXP>
+__device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int p_stride, int t_stride, int t, double inv_lambda, double &m,
+                                                 double &S, double &A, double &B, double &DL, double &DR)
+{
+  constexpr int kPer = 2;                                   // partials held in registers per thread (one L2 round trip)
+  constexpr int NWARP = NT / 32;
+  __shared__ double red[NWARP][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  const double *base = partials + (size_t)t * t_stride;
+  double2 c0[kPer], c1[kPer], c2[kPer];
+  m = inf;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    const int p = threadIdx.x + i * NT;
+    c0[i] = make_double2(inf, 0.0); c1[i] = make_double2(0.0, 0.0); c2[i] = make_double2(0.0, 0.0);
+    if (p < n_partials) {
+      const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
+      c0[i] = __ldcg(c); c1[i] = __ldcg(c + 1); c2[i] = __ldcg(c + 2);
+    }
+    m = fmin(m, c0[i].x);
+  }
+  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) m = fmin(m, __ldcg(base + (size_t)p * p_stride));
+  m = warp_min(m);
+  if (lane == 0) red[warp][0] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int w = 1; w < NWARP; w++) m = fmin(m, red[w][0]);
+  S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    if (c0[i].x != inf) {
+      const double f = (c0[i].x == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - c0[i].x) * inv_lambda);
+      S = fma(c0[i].y, f, S); A = fma(c1[i].x, f, A); B = fma(c1[i].y, f, B);
+    }
+    DL += c2[i].x; DR += c2[i].y;
+  }
+  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) {
+    const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
+    const double2 d0 = __ldcg(c), d1 = __ldcg(c + 1), d2 = __ldcg(c + 2);
+    if (d0.x != inf) {
+      const double f = (d0.x == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - d0.x) * inv_lambda);
+      S = fma(d0.y, f, S); A = fma(d1.x, f, A); B = fma(d1.y, f, B);
+    }
+    DL += d2.x; DR += d2.y;
+  }
+  S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
+  __syncthreads();
+  if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < NWARP; w++) {
+      S += red[w][1]; A += red[w][2]; B += red[w][3]; DL += red[w][4]; DR += red[w][5];
+    }
+  }
+}
+
+// a merger CTA of the fused call: step t = blockIdx.x - n_roll
+template <int NT, bool FASTEXP>
+__device__ __forceinline__ void mppi_merger(const MppiArgs &a)
+{
+  const int t = (int)blockIdx.x - a.n_roll;
+  // the next grid in the stream (the kernel that draws the next call's variates) may take the SMs the rollout CTAs leave
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // every rollout CTA of this call has published its partial (a monotonic count over the handle's fused calls)
+  if (threadIdx.x == 0) {
+    unsigned long long seen;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.arrive) : "memory");
+      if (seen >= a.arrive_need) break;
+      if (++spins == (1u << 28)) __trap();
+    }
+  }
+  __syncthreads();
+  mppi_stamp(a, 4);
+  double m, S, A, B, DL, DR;
+  mppi_block_merge<NT, FASTEXP>(a.partials, a.n_roll, 6, 6 * a.n_roll, t, a.inv_lambda, m, S, A, B, DL, DR);
+  mppi_stamp(a, 5);
+  if (threadIdx.x == 0) {
+    double *o = a.merged + (size_t)t * 6;
+    o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
+  }
+  if (a.nranks > 1) mppi_exchange_step<NT, FASTEXP>(a, t, m, S, A, B, DL, DR);
+  if (threadIdx.x != 0) return;
+  mppi_apply_update(a, a.u_plan, t, m, S, A, B, DL, DR);
+  // this step of the plan is complete: the next call's CTAs wait for all T
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.plan_seq), "l"(1ull) : "memory");
+  mppi_stamp(a, 6);
+}
+
+// dynamic shared memory of the rollout kernel:
+//   [warps][2][32*S*3] fp32 staging rows of the state tensor (after the loop: merge scratch, [threads*6] doubles)
+//   [S*4][threads]     fp64 online-softmax accumulators (min J, sum e, sum e*duL, sum e*duR) per owned step
+//   [S/2][threads]     float4 sums of the binary32 variates (sum duL, sum duR before the scaling by sigma)
+//   [2][G*S]           the control plan
+//   [warps][32*S]      fp64 cost-to-go and float2 variates of the rollouts in flight, for the transposition in front of the
+//                      softmax (production variants)
+//   [S*2][threads]     fp64 sum duL / sum duR (generic variant only)
+//   [tile][tile]       fp32 obstacle-field tile (obstacle variants only)
+__host__ __device__ constexpr size_t mppi_dz_bytes(int S) { return (size_t)S * 8; }
+__host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW, bool obs, bool fast)
+{
+  return (size_t)NW * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 4 * NW * 32 * sizeof(double) + (size_t)NW * 32 * mppi_dz_bytes(S) +
+         (size_t)2 * G * S * sizeof(double) + (fast ? (size_t)NW * 32 * S * (sizeof(double) + sizeof(float2)) : (size_t)S * 2 * NW * 32 * sizeof(double)) +
+         (obs ? (size_t)kMppiObsTile * kMppiObsTile * sizeof(float) + 16 : 0);
+}
+// CTAs per SM the register budget is cut for: 8-warp CTAs run three to an SM (80 registers), 10-warp CTAs two and 20-warp CTAs
+// one (20 warps per SM, 96 registers: no spills in the rollout loop)
+__host__ __device__ constexpr int mppi_min_blocks(int S, int NW) { return NW >= 16 ? 1 : (NW >= 10 ? 2 : (S >= 8 ? 1 : 3)); }
+
+// FAST = the production configuration, decided on the host: own noise DRAWN AHEAD by mppi_noise_kernel, no capture taps,
+// T == G * S (no partially filled lanes), TMA row stores, and half-step heading increments provably inside the Taylor range.  OBS adds the obstacle term
+// (the generic variant takes it from a.obs_on).  NW = warps per CTA.
+template <int S, int G, bool FAST, bool OBS, int NW>
+__global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_kernel(const __grid_constant__ MppiArgs a)
+{
+  constexpr int NT = NW * 32;
   static_assert(S % 2 == 0 && (G == 8 || G == 16 || G == 32), "a Philox call covers two steps; G lanes per rollout");
+  if (a.tail && (int)blockIdx.x >= a.n_roll) {
+    mppi_merger<NT, FAST>(a);
+    return;
+  }
   constexpr int R = 32 / G;        // rollouts a warp carries at a time
   constexpr int TP = G * S;        // padded horizon
+  constexpr int NBUF = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr size_t kStageBytes = (size_t)NW * NBUF * 32 * S * 3 * 4, kAccBytes = (size_t)S * 4 * NT * 8, kDzBytes = (size_t)NT * mppi_dz_bytes(S),
+                   kPlanBytes = (size_t)2 * TP * 8, kDaccBytes = FAST ? (size_t)NT * S * 16 : (size_t)S * 2 * NT * 8;
+  static_assert((size_t)NT * 48 <= kStageBytes, "the merge scratch lives in the staging rows");
   float *stage_base = reinterpret_cast<float *>(smem_raw);                                       // [warps][2][R*TP*3]
-  constexpr int NBUF = mppi_stage_buffers(NW);
-  double *acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * NBUF * 32 * S * 3 * 4) + threadIdx.x;   // [S*6][threads]
-  double *cta_acc = reinterpret_cast<double *>(smem_raw + kMppiWarps * NBUF * 32 * S * 3 * 4);             // (epilogue)
+  double *scratch = reinterpret_cast<double *>(smem_raw);                                        // [NT*6], after the loop
+  double *acc_base = reinterpret_cast<double *>(smem_raw + kStageBytes);                         // [S*4][threads]
+  double *acc = acc_base + threadIdx.x;
+  float4 *dz4 = reinterpret_cast<float4 *>(smem_raw + kStageBytes + kAccBytes);                  // [S/2][threads]
+  double *plan = reinterpret_cast<double *>(smem_raw + kStageBytes + kAccBytes + kDzBytes);      // [2][TP]
+  double *dacc = reinterpret_cast<double *>(smem_raw + kStageBytes + kAccBytes + kDzBytes + kPlanBytes);     // [S*2][threads], generic only
+  double *jbuf = dacc;                                                                                      // [warps][R][TP], production only
+  float2 *zsm = reinterpret_cast<float2 *>(jbuf + (size_t)NW * R * TP);                                     // [warps][R][TP] (zL, zR), production only
+  float *tile = reinterpret_cast<float *>(smem_raw + kStageBytes + kAccBytes + kDzBytes + kPlanBytes + kDaccBytes);
+  uint64_t *tile_bar = reinterpret_cast<uint64_t *>(tile + kMppiObsTile * kMppiObsTile);
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = lane & (G - 1);    // position inside the rollout's lane group
   const int r = lane / G;          // which of the warp's R rollouts
-  const int gw = blockIdx.x * kMppiWarps + warp;
-  const int nw = gridDim.x * kMppiWarps;
+  const int gw = blockIdx.x * NW + warp;
+  const int nw = a.n_roll * NW;
   const int T = FAST ? TP : a.T;
   const int t0 = g * S;            // first owned step
-  const bool ext_noise = !FAST && a.external_noise, capture = !FAST && a.capture, obs_on = !FAST && a.obs_on;
+  const bool ext_noise = !FAST && a.external_noise, capture = !FAST && a.capture, obs_on = OBS || (!FAST && a.obs_on);
   const bool tma_store = FAST || a.tma_store;
   float *stage = stage_base + warp * NBUF * (R * TP * 3);
 
   const double sin0 = a.sin0, cos0 = a.cos0;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
 
-  // online-softmax accumulators of this lane's steps: (min J, sum e, sum e*duL, sum e*duR, sum duL, sum duR) x S
+  // online-softmax accumulators of this lane's steps: (min J, sum e, sum e*duL, sum e*duR) x S in shared memory, with
+  // the high word of (min J + cut) in a register: a cost-to-go above it cannot contribute
 #pragma unroll
   for (int s = 0; s < S; s++) {
-    acc[(s * 6 + 0) * kMppiThreads] = inf;
+    acc[(s * 4 + 0) * NT] = inf;
 #pragma unroll
-    for (int j = 1; j < 6; j++) acc[(s * 6 + j) * kMppiThreads] = 0.0;
+    for (int j = 1; j < 4; j++) acc[(s * 4 + j) * NT] = 0.0;
+  }
+  int thr_hi[S];
+  // sum duL, sum duR take part in the update only through the +1e-8 weight floor (mppi.cpp:117): the production variant
+  // sums the binary32 variates themselves in shared memory (one 16-byte load / store per two steps; scaled by sigma once,
+  // at the end), the generic one the fp64 perturbations
+  double sDL[FAST ? 1 : S], sDR[FAST ? 1 : S];
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    thr_hi[s] = 0x7FF00000;
+    if (!FAST) { sDL[s] = 0.0; sDR[s] = 0.0; }
+  }
+#pragma unroll
+  for (int s = 0; s < S; s += 2) dz4[(s / 2) * NT + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // the variates of a call do not depend on the plan.  Production: mppi_noise_kernel drew them AHEAD (right behind the
+  // previous call, off this call's critical path) and the loop loads them, 16 bytes per two steps.  Otherwise they are drawn
+  // in the loop, the first pass's before the wait below so that it overlaps the previous call's tail
+  constexpr bool z_ahead = FAST;
+  float zq[S * 2];
+  int base = gw * R;
+  if (!ext_noise && !z_ahead && base < a.K) {
+#pragma unroll
+    for (int s = 0; s < S; s += 2) mppi_normal_quad(a, (uint32_t)(a.k_offset + base + r), (uint32_t)((t0 + s) >> 1), &zq[2 * s]);
   }
 
-  // launched programmatically dependent on the previous call's update kernel: everything above overlapped its tail;
-  // the plan it writes is read from here on
+  // launched programmatically dependent on the previous call: everything above overlapped its tail; the plan it writes
+  // is read from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the grid in front of this one may be the kernel that drew this call's variates: the call before THAT one counts its
+  // finished plan steps (normally long there)
+  if (a.plan_need && threadIdx.x == 0) {
+    unsigned long long seen;
+    unsigned spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.plan_seq) : "memory");
+      if (++spins == (1u << 28)) __trap();
+    } while (seen < a.plan_need);
+  }
+  __syncthreads();
+  // the obstacle-field tile around the start pose (occupancy-grid tiles staged through TMA, north_star): rows of the tile
+  // are contiguous in the field, one bulk copy each, all completing on one mbarrier.  After the wait: the field may have
+  // been written by the kernel that precedes this one in the stream (b2n_pf_write_distance_field)
+  if (obs_on && a.obs_ti0 >= 0 && threadIdx.x == 0) {
+    mbar_init(tile_bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(tile_bar, kMppiObsTile * kMppiObsTile * sizeof(float));
+    for (int i = 0; i < kMppiObsTile; i++)
+      tma_load_1d(tile + i * kMppiObsTile, a.obs_dist + (size_t)(a.obs_ti0 + i) * a.obs_ysize + a.obs_tj0, kMppiObsTile * sizeof(float), tile_bar);
+  }
+  for (int i = threadIdx.x; i < 2 * TP; i += NT) {
+    const int row = i / TP, t = i - row * TP;
+    plan[i] = t < T ? a.u_plan[row * T + t] : 0.0;        // plain (coherent) loads: the previous call's tail wrote this buffer
+  }
+  __syncthreads();
+  if (obs_on && a.obs_ti0 >= 0) mbar_wait(tile_bar, 0);
+
+  mppi_stamp(a, 0);
+  float4 zn[FAST ? S / 2 : 1];
+  if (z_ahead && base < a.K) {
+    const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
+#pragma unroll
+    for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
+  }
   int buf = 0;
-  for (int base = gw * R; base < a.K; base += nw * R, buf ^= (NBUF - 1)) {
+  bool have_noise = true;
+  for (; base < a.K; base += nw * R, buf ^= 1) {
     const int k = base + r;
     const bool live = k < a.K;
+    const bool first = base == gw * R + nw * R;      // (the SECOND pass: thresholds set, steady state)
+    mppi_clock(a, first, 8);
 
-    // ---- perturbed controls (mppi.cpp:84-93,173-184), per-step increments, half-step rotations ----------
-    double duL[S], duR[S], cc[S], vh[S], dth[S], cd[S], sd[S];
-    double tc = 1.0, ts = 0.0, tth = 0.0;      // this lane's total rotation and heading change
+    // ---- perturbed controls (mppi.cpp:84-93,173-184) and the lane's S steps integrated in the lane's OWN frame -----
+    // (heading 0 and position 0 at the lane's first step; the scans below place the lane in the world).  RK4 with the
+    // control held over the step (rk4.cpp:95-115): k1 at the step's heading, k2 = k3 at heading + h w / 2, k4 at
+    // heading + h w, so with d = h w / 2 the bracket (k1 + 2 k2 + 2 k3 + k4) is R (1 + 4 e^{id} + e^{2id}) =
+    // R e^{id} (4 + 2 cos d): the mid-step heading, scaled.  sin d, cos d come from a short Taylor series.
+    if (z_ahead) {
+      // (loaded one pass ahead, below: an L2 round trip is most of a thousand cycles)
 #pragma unroll
-    for (int s = 0; s < S; s += 2) {
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!ext_noise)
-        normal_quad_f32(a.seed_lo, a.seed_hi, kDomainMppi, a.call, (uint32_t)(a.k_offset + k), (uint32_t)((t0 + s) >> 1), z);
+      for (int s = 0; s < S; s += 2) { zq[2 * s] = zn[s / 2].x; zq[2 * s + 1] = zn[s / 2].y; zq[2 * s + 2] = zn[s / 2].z; zq[2 * s + 3] = zn[s / 2].w; }
+    } else if (!have_noise && !ext_noise) {
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int t = t0 + s + j;
-        const bool act = FAST || t < T;
-        double l = 0.0, rr = 0.0, p0 = 0.0, p1 = 0.0;
-        if (act) {
-          p0 = __ldg(&a.u_plan[t]);
-          p1 = __ldg(&a.u_plan[T + t]);
-          if (ext_noise) {
-            if (live) {
-              const double2 e = __ldg(reinterpret_cast<const double2 *>(a.ext) + ((size_t)k * T + t));
-              l = e.x; rr = e.y;
-            }
-          } else {
-            l = (double)z[2 * j] * a.sigL;
-            rr = (double)z[2 * j + 1] * a.sigR;
-          }
-        }
-        duL[s + j] = l; duR[s + j] = rr;
-        const double uL = p0 + l, uR = p1 + rr;                 // NOT clamped (mppi.cpp:93)
-        cc[s + j] = (uL * a.R[0]) * uL + (uR * a.R[1]) * uR;    // u^T R u (mppi.hpp:92)
-        vh[s + j] = a.c_v * (uL + uR);                          // (h/6) v, v = (r/2)(uL + uR)   (mppi.hpp:45-46)
-        dth[s + j] = a.c_w * (uR - uL);                         // h w, w = (r/L)(uR - uL): rk4.cpp:114 with k1 = k2 = k3 = k4
-        mppi_sincos_small<FAST>(0.5 * dth[s + j], sd[s + j], cd[s + j]);
-        // product of the lane's HALF-step rotations (squared once below: rotations commute)
-        const double nc = tc * cd[s + j] - ts * sd[s + j];
-        ts = fma(tc, sd[s + j], ts * cd[s + j]);
-        tc = nc;
-        tth += dth[s + j];
+      for (int s = 0; s < S; s += 2) mppi_normal_quad(a, (uint32_t)(a.k_offset + k), (uint32_t)((t0 + s) >> 1), &zq[2 * s]);
+    }
+    have_noise = false;
+    mppi_clock(a, first, 9);
+    if (FAST) {
+      // the rollout's variates by step, for the lanes that keep the steps' accumulators (softmax below)
+      float4 *zrow = reinterpret_cast<float4 *>(zsm + (size_t)(warp * R + r) * TP + t0);
+#pragma unroll
+      for (int s = 0; s < S; s += 2) zrow[s / 2] = make_float4(zq[2 * s], zq[2 * s + 1], zq[2 * s + 2], zq[2 * s + 3]);
+    }
+    if (FAST && live) {
+#pragma unroll
+      for (int s = 0; s < S; s += 2) {
+        float4 d = dz4[(s / 2) * NT + threadIdx.x];
+        d.x += zq[2 * s]; d.y += zq[2 * s + 1]; d.z += zq[2 * s + 2]; d.w += zq[2 * s + 3];
+        dz4[(s / 2) * NT + threadIdx.x] = d;
       }
     }
-    {
-      // the lane's total rotation = (product of half steps)^2
-      const double nc = fma(tc, tc, -(ts * ts));
-      ts = 2.0 * (ts * tc);
-      tc = nc;
+    mppi_clock(a, first, 10);
+    double duL[FAST ? 1 : S], duR[FAST ? 1 : S];   // the production variant re-derives the perturbation from its variate where needed
+    double cc[S], lx[S], ly[S], thc[S];
+    double tc = 1.0, ts = 0.0, tth = 0.0;      // rotation and heading change of the lane so far
+    double ax = 0.0, ay = 0.0;                 // displacement in the lane's frame so far
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int t = t0 + s;
+      const bool act = FAST || t < T;
+      double l = 0.0, rr = 0.0;
+      const double p0 = plan[t], p1 = plan[TP + t];
+      if (act) {
+        if (ext_noise) {
+          if (live) {
+            const double2 e = __ldg(reinterpret_cast<const double2 *>(a.ext) + ((size_t)k * T + t));
+            l = e.x; rr = e.y;
+          }
+        } else {
+          l = (double)zq[2 * s] * a.sigL;
+          rr = (double)zq[2 * s + 1] * a.sigR;
+        }
+      }
+      if (!FAST) { duL[s] = l; duR[s] = rr; }
+      const double uL = p0 + l, uR = p1 + rr;                 // NOT clamped (mppi.cpp:93)
+      cc[s] = (uL * a.R[0]) * uL + (uR * a.R[1]) * uR;        // u^T R u (mppi.hpp:92)
+      const double vh = a.c_v * (uL + uR);                    // (h/6) v, v = (r/2)(uL + uR)   (mppi.hpp:45-46)
+      const double dth = a.c_w * (uR - uL);                   // h w, w = (r/L)(uR - uL): rk4.cpp:114 with k1 = k2 = k3 = k4
+      double sd, cd;
+      mppi_sincos_small<FAST>(a, 0.5 * dth, sd, cd);
+      const double mc = fma(tc, cd, -(ts * sd)), ms = fma(tc, sd, ts * cd);      // mid-step heading
+      const double f = vh * fma(2.0, cd, 4.0);
+      ax = fma(f, mc, ax);
+      ay = fma(f, ms, ay);
+      lx[s] = ax; ly[s] = ay;
+      tc = fma(mc, cd, -(ms * sd)); ts = fma(mc, sd, ms * cd);                   // end-of-step heading
+      tth += dth;
+      thc[s] = tth;
     }
 
+    mppi_clock(a, first, 11);
     // ---- segmented inclusive scans over the rollout's G lanes: rotation product and heading sum ----------
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const double oc = __shfl_up_sync(kFullMask, tc, d, G), os = __shfl_up_sync(kFullMask, ts, d, G);
-      const double ot = __shfl_up_sync(kFullMask, tth, d, G);
-      if (g >= d) {
-        const double nc = tc * oc - ts * os;
-        ts = fma(tc, os, ts * oc);
-        tc = nc;
-        tth += ot;
-      }
-    }
-    // exclusive prefix, seeded with the start heading
-    double rc = __shfl_up_sync(kFullMask, tc, 1, G), rs = __shfl_up_sync(kFullMask, ts, 1, G);
-    double th = __shfl_up_sync(kFullMask, tth, 1, G);
-    if (g == 0) { rc = 1.0; rs = 0.0; th = 0.0; }
+    for (int d = 1; d < G; d <<= 1) scan_rot_up<G>(tc, ts, tth, d);
+    // exclusive prefix, seeded with the start heading: the world heading at the lane's first step
+    double rc = shift1<G, true>(tc, 1.0), rs = shift1<G, true>(ts, 0.0);
+    const double th = shift1<G, true>(tth, 0.0) + a.x0[2];
     {
-      const double nc = rc * cos0 - rs * sin0;
+      const double nc = fma(rc, cos0, -(rs * sin0));
       rs = fma(rc, sin0, rs * cos0);
       rc = nc;
     }
 
-    // ---- RK4 position increments: k1 at theta, k2 = k3 at theta + h w / 2, k4 at theta + h w (rk4.cpp:95-115) ----
-    double px[S], py[S], TH[S];
-    double ax = 0.0, ay = 0.0;
+    mppi_clock(a, first, 12);
+    // ---- position: the lane's displacement turned into the world frame, segmented prefix sums ----------------------
+    double ix = fma(rc, ax, -(rs * ay)), iy = fma(rs, ax, rc * ay);
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-      const double mc = rc * cd[s] - rs * sd[s], ms = fma(rc, sd[s], rs * cd[s]);      // mid-step heading
-      const double ec = mc * cd[s] - ms * sd[s], es = fma(mc, sd[s], ms * cd[s]);      // end-of-step heading
-      // (h/6) v (k1 + 2 k2 + 2 k3 + k4): with the headings theta, theta + d, theta + 2 d the bracket is
-      // R (1 + 4 e^{id} + e^{2id}) = R e^{id} (4 + 2 cos d) - the mid-step heading scaled; running sum inside the lane
-      const double f = vh[s] * fma(2.0, cd[s], 4.0);
-      ax = fma(f, mc, ax);
-      ay = fma(f, ms, ay);
-      px[s] = ax; py[s] = ay;
-      th += dth[s];
-      TH[s] = a.x0[2] + th;
-      rc = ec; rs = es;
-    }
+    for (int d = 1; d < G; d <<= 1) scan_add2_up<G>(ix, iy, d);
+    const double ex = shift1<G, true>(ix, 0.0) + a.x0[0], ey = shift1<G, true>(iy, 0.0) + a.x0[1];
 
-    // ---- position: segmented prefix sums -------------------------------------------------------------------
-    double ix = ax, iy = ay;
-#pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const double ox = __shfl_up_sync(kFullMask, ix, d, G), oy = __shfl_up_sync(kFullMask, iy, d, G);
-      if (g >= d) { ix += ox; iy += oy; }
-    }
-    double ex = __shfl_up_sync(kFullMask, ix, 1, G), ey = __shfl_up_sync(kFullMask, iy, 1, G);
-    if (g == 0) { ex = 0.0; ey = 0.0; }
-    ex += a.x0[0]; ey += a.x0[1];
-
+    mppi_clock(a, first, 13);
     // ---- states after each step -> staging row; loss (mppi.cpp:99-105, mppi.hpp:87-105) -------------------
     float *row = stage + buf * (R * TP * 3) + r * (T * 3);
     if (tma_store) {
       if (lane == 0) tma_store_wait_read<NBUF - 1>();   // the store that last used this buffer has drained it
       __syncwarp();
     }
+    mppi_clock(a, first, 14);
     double J[S];
     double rj = 0.0;
+    float st[S * 3];
 #pragma unroll
     for (int s = S - 1; s >= 0; s--) {
       const int t = t0 + s;
-      const double X = ex + px[s], Y = ey + py[s];
+      const double X = fma(rc, lx[s], fma(-rs, ly[s], ex)), Y = fma(rs, lx[s], fma(rc, ly[s], ey));
+      const double TH = th + thc[s];
       double l = 0.0;
+      st[s * 3 + 0] = (float)X; st[s * 3 + 1] = (float)Y; st[s * 3 + 2] = (float)TH;
       if (FAST || t < T) {
-        row[t * 3 + 0] = (float)X;
-        row[t * 3 + 1] = (float)Y;
-        row[t * 3 + 2] = (float)TH[s];
-        const double e0 = X - a.xd[0], e1 = Y - a.xd[1], e2 = TH[s] - a.xd[2];   // theta NOT wrapped
+        const double e0 = X - a.xd[0], e1 = Y - a.xd[1], e2 = TH - a.xd[2];   // theta NOT wrapped
         if (t < T - 1) l = ((e0 * a.Q[0]) * e0 + (e1 * a.Q[1]) * e1 + (e2 * a.Q[2]) * e2) + cc[s];
         else l = (e0 * a.P1[0]) * e0 + (e1 * a.P1[1]) * e1 + (e2 * a.P1[2]) * e2;   // replaces the running loss
-        if (obs_on) l += mppi_obstacle_cost(a, X, Y);
+        if (obs_on) l += mppi_obstacle_cost(a, tile, X, Y);
       }
       rj += l;
       J[s] = rj;                                  // suffix sum inside the lane (cumSumCost, mppi.cpp:15-25)
     }
+    if (FAST) {
+      // the lane's S states are 12 S contiguous bytes of the row: vector stores
+      if ((S * 3) % 4 == 0) {
+        float4 *dst = reinterpret_cast<float4 *>(row + t0 * 3);
+#pragma unroll
+        for (int i = 0; i < S * 3 / 4; i++) dst[i] = make_float4(st[4 * i], st[4 * i + 1], st[4 * i + 2], st[4 * i + 3]);
+      } else {
+        float2 *dst = reinterpret_cast<float2 *>(row + t0 * 3);
+#pragma unroll
+        for (int i = 0; i < S * 3 / 2; i++) dst[i] = make_float2(st[2 * i], st[2 * i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; s++)
+        if (t0 + s < T) { row[(t0 + s) * 3 + 0] = st[s * 3]; row[(t0 + s) * 3 + 1] = st[s * 3 + 1]; row[(t0 + s) * 3 + 2] = st[s * 3 + 2]; }
+    }
 
+    mppi_clock(a, first, 15);
+    if (z_ahead && base + nw * R < a.K) {
+      // the next pass's variates: in flight during the scan and the softmax below
+      const float4 *zr = a.zbuf + ((size_t)min(base + nw * R + r, a.K - 1) * (TP / 2) + (t0 >> 1));
+#pragma unroll
+      for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
+    }
     // ---- cost-to-go: segmented suffix sum over the lanes ---------------------------------------------------
     double ij = rj;
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const double oj = __shfl_down_sync(kFullMask, ij, d, G);
-      if (g + d < G) ij += oj;
-    }
-    double ej = __shfl_down_sync(kFullMask, ij, 1, G);
-    if (g == G - 1) ej = 0.0;
+    for (int d = 1; d < G; d <<= 1) scan_add_down<G>(ij, d);
+    const double ej = shift1<G, false>(ij, 0.0);
 
-    // ---- online softmax over rollouts, one accumulator set per owned step ---------------------------------
+    mppi_clock(a, first, 16);
+    // ---- online softmax over rollouts, one accumulator set per step ---------------------------------------------------
+    // Production variants TRANSPOSE first: lane g simulated steps gS .. gS + S - 1, but keeps the accumulators of steps
+    // g, G + g, 2G + g, ...  Which steps of the horizon are "soft" (many rollouts within the exponent range of the
+    // minimum) depends on the step, not on the rollout: with the simulation's ownership they all sit in one or two lanes
+    // of a group and the warp walks through every one of its S accumulator blocks for them; transposed they share one
+    // slot across the lanes and the other blocks are skipped by the whole warp.
+    double Jt[S];
+    if (FAST) {
+      double *jb = jbuf + (size_t)(warp * R + r) * TP;
+#pragma unroll
+      for (int s = 0; s < S; s += 2) *reinterpret_cast<double2 *>(jb + t0 + s) = make_double2(J[s] + ej, J[s + 1] + ej);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < S; s++) Jt[s] = jb[s * G + g];
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; s++) Jt[s] = J[s] + ej;
+    }
 #pragma unroll
     for (int s = 0; s < S; s++) {
-      const double Js = J[s] + ej;
-      if (live && (FAST || t0 + s < T)) {
-        double *c = acc + s * 6 * kMppiThreads;
-        const double m0 = c[0];
-        const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
-        const double e = mppi_exp_neg(-fabs(d));
-        const bool newmin = d > 0.0;
-        // a rollout whose weight underflows against the running minimum leaves the three sums untouched - at the
-        // shipped temperature that is nearly every term, and the accumulators stay in shared memory unread
-        if (newmin || e != 0.0) {
-          const double S0 = c[kMppiThreads], A0 = c[2 * kMppiThreads], B0 = c[3 * kMppiThreads];
-          const double scale = newmin ? e : 1.0, add = newmin ? 1.0 : e;
-          c[kMppiThreads] = fma(S0, scale, add);
-          c[2 * kMppiThreads] = fma(A0, scale, add * duL[s]);
-          c[3 * kMppiThreads] = fma(B0, scale, add * duR[s]);
-          if (newmin) c[0] = Js;
+      const double Js = Jt[s];
+      const int ts = FAST ? s * G + g : t0 + s;      // the step this accumulator set belongs to
+      if (live && (FAST || ts < T)) {
+        if (!FAST) { sDL[s] += duL[s]; sDR[s] += duR[s]; }
+        // J >= 0, so the high words order like the values: one integer compare against the register threshold decides
+        // whether this rollout can matter for the step (at the shipped temperature it rarely does)
+        if (__double2hiint(Js) <= thr_hi[s]) {
+          double *c = acc + s * 4 * NT;
+          const double m0 = c[0];
+          const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
+          const bool newmin = d > 0.0;
+          const double e = mppi_exp_neg<FAST>(-fabs(d));
+          if (newmin || e != 0.0) {
+            double l, rr;
+            if (FAST) {
+              // the step's perturbation, re-derived from its variates (left in shared memory by the simulating lane)
+              const float2 q = zsm[(size_t)(warp * R + r) * TP + ts];
+              l = (double)q.x * a.sigL;
+              rr = (double)q.y * a.sigR;
+            } else {
+              l = duL[s]; rr = duR[s];
+            }
+            if (newmin) {
+              // (rare) the sums are rescaled to the new minimum
+              c[NT] = fma(c[NT], e, 1.0);
+              c[2 * NT] = fma(c[2 * NT], e, l);
+              c[3 * NT] = fma(c[3 * NT], e, rr);
+              c[0] = Js;
+              if (a.thr_on) thr_hi[s] = __double2hiint(Js + a.cut_lambda) + 1;
+            } else {
+              c[NT] += e;
+              c[2 * NT] = fma(e, l, c[2 * NT]);
+              c[3 * NT] = fma(e, rr, c[3 * NT]);
+            }
+          }
         }
-        c[4 * kMppiThreads] += duL[s];
-        c[5 * kMppiThreads] += duR[s];
         if (capture) {
           a.J_out[(size_t)k * T + t0 + s] = Js;
           reinterpret_cast<double2 *>(a.du_out)[(size_t)k * T + t0 + s] = make_double2(duL[s], duR[s]);
@@ -338,6 +937,7 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 && NW != 7 ? 3 
       }
     }
 
+    mppi_clock(a, first, 17);
     // ---- the state tensor: the warp's rows are contiguous in [K][T][3]; one bulk store ---------------------
     const int nlive = min(R, a.K - base);
     float *gdst = a.states + (size_t)base * T * 3;
@@ -354,157 +954,104 @@ __global__ void __launch_bounds__(NW * 32, (S >= 8 ? 1 : (S >= 4 && NW != 7 ? 3 
       for (int i = lane; i < nlive * T * 3; i += 32) gdst[i] = ssrc[i];
       __syncwarp();
     }
+    mppi_clock(a, first, 18);
   }
-  // the rollouts are done: let the dependent grid (the update kernel) be scheduled while this CTA merges; it blocks in
-  // griddepcontrol.wait until this whole grid has completed and its partials are visible
+  // the rollouts are done: let the dependent grid (the next call) be scheduled while this CTA merges; it blocks in
+  // griddepcontrol.wait until this whole grid has completed and the plan is visible
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tma_store && lane == 0) tma_store_wait<0>();
-
-  // ---- merge the CTA's accumulator sets per time step: minimum first, then every set rescaled ONCE -----------------
-  // (two passes instead of pairwise softmax merges: one exponential per set, all of them independent).  Lane groups
-  // of a warp combine by xor-shuffles, warps through shared memory laid out [.][warp][g] so that lanes read
-  // consecutive words.
-  double am[S], aS[S], aA[S], aB[S], aDL[S], aDR[S];
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    const double *c = acc + s * 6 * kMppiThreads;
-    am[s] = c[0]; aS[s] = c[kMppiThreads]; aA[s] = c[2 * kMppiThreads]; aB[s] = c[3 * kMppiThreads];
-    aDL[s] = c[4 * kMppiThreads]; aDR[s] = c[5 * kMppiThreads];
-  }
-  double *smin = reinterpret_cast<double *>(smem_raw);     // [S][warps][G], over the staging rows
-  double *ssum = cta_acc;                                   // [S][warps][5][G], over the accumulator area
   __syncthreads();      // every warp has left the loop and drained its bulk stores: the staging rows are free
+  mppi_stamp(a, 1);
+
+  // ---- merge the CTA's accumulator sets per time step -----------------------------------------------------------------
+  if (!FAST) {
 #pragma unroll
-  for (int s = 0; s < S; s++) {
-    double m = am[s];
-#pragma unroll
-    for (int off = G; off < 32; off <<= 1) m = fmin(m, __shfl_xor_sync(kFullMask, m, off));
-    if (r == 0) smin[(s * kMppiWarps + warp) * G + g] = m;
-  }
-  __syncthreads();      // every thread has read its accumulators: their area may be overwritten from here on
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    double m = smin[(s * kMppiWarps) * G + g];
-#pragma unroll
-    for (int w = 1; w < kMppiWarps; w++) m = fmin(m, smin[(s * kMppiWarps + w) * G + g]);
-    // an empty set has min = +inf and zero sums
-    const double f = (am[s] == inf) ? 0.0 : ((am[s] == m) ? 1.0 : mppi_exp_neg((m - am[s]) * a.inv_lambda));
-    double v[5] = {aS[s] * f, aA[s] * f, aB[s] * f, aDL[s], aDR[s]};
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-#pragma unroll
-      for (int off = G; off < 32; off <<= 1) v[j] += __shfl_xor_sync(kFullMask, v[j], off);
-      if (r == 0) ssum[((s * kMppiWarps + warp) * 5 + j) * G + g] = v[j];
+    for (int s = 0; s < S; s++) {
+      dacc[(s * 2 + 0) * NT + threadIdx.x] = sDL[s];
+      dacc[(s * 2 + 1) * NT + threadIdx.x] = sDR[s];
     }
-    am[s] = m;
+    __syncthreads();
   }
+  // power of two >= T, at most NT
+  int TP2 = 1;
+  while (TP2 < T) TP2 <<= 1;
+  const int x = threadIdx.x;
+  // set i of step t = the accumulators of lane group (warp i / R, rollout slot i % R) for step t: in the production
+  // variants lane t mod G holds them in slot t / G (transposed, see the softmax above), the sums of the variates stay with
+  // the lane that simulated the step (lane t / S, slot t mod S)
+  auto grp = [&](int i) { return (i / R) * 32 + (i % R) * G; };
+  auto cta_min = [&](int t, int i) { return FAST ? acc_base[((t / G) * 4) * NT + grp(i) + t % G] : acc_base[((t % S) * 4) * NT + grp(i) + t / S]; };
+  auto cta_set = [&](int t, int i, double v[6]) {
+    const int tid_a = grp(i) + (FAST ? t % G : t / S), sa = FAST ? t / G : t % S;
+    const int tid_d = grp(i) + t / S, sd = t % S;
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = acc_base[(sa * 4 + j) * NT + tid_a];
+    if (FAST) {
+      const float2 z = reinterpret_cast<const float2 *>(dz4 + (sd / 2) * NT + tid_d)[sd & 1];
+      v[4] = (double)z.x * a.sigL; v[5] = (double)z.y * a.sigR;
+    } else {
+      v[4] = dacc[(sd * 2) * NT + tid_d]; v[5] = dacc[(sd * 2 + 1) * NT + tid_d];
+    }
+  };
+  double v[6];
+  mppi_merge_sets<NT, FAST>(T, TP2, NW * R, a.inv_lambda, scratch, cta_min, cta_set, v);
+  const int n_cta = a.n_roll;
+  if (x < T) {
+    double *o = a.partials + ((size_t)x * n_cta + blockIdx.x) * 6;
+    reinterpret_cast<double2 *>(o)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2 *>(o)[1] = make_double2(v[2], v[3]);
+    reinterpret_cast<double2 *>(o)[2] = make_double2(v[4], v[5]);
+  }
+  mppi_stamp(a, 2);
+  if (!a.tail) return;
+  // count this CTA in: a release reduction by one thread after the barrier covers every thread's stores, and there is
+  // nothing to wait for - the merger CTAs watch the count
   __syncthreads();
-  if (threadIdx.x < TP) {
-    const int ss = threadIdx.x / G, gg = threadIdx.x % G;
-    const int t = gg * S + ss;
-    if (t < T) {
-      double m = smin[(ss * kMppiWarps) * G + gg];
+  if (x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.arrive), "l"(1ull) : "memory");
+  mppi_stamp(a, 3);
+}
+
+// ---- the variates of the NEXT call, drawn ahead ------------------------------------------------------------------------
+// One thread per Philox call = two time steps of one rollout: [K][T/2] float4 (zL_t, zR_t, zL_t+1, zR_t+1), the values
+// mppi_normal_quad would produce inside the rollout loop, bit for bit.  Launched right behind a call's kernel with
+// programmatic dependent launch: its CTAs fill the SMs that the call's early finishers leave (the tail of the call - the
+// last passes, the merge tree - runs on a few CTAs), and in a control loop it runs while the host turns the pose around.
+struct MppiNoiseArgs
+{
+  float4 *zbuf;
+  int K, half_T, k_offset;
+  uint32_t call;
+  uint32_t key0[10], key1[10];
+};
+
+__global__ void __launch_bounds__(256) mppi_noise_kernel(const __grid_constant__ MppiNoiseArgs n)
+{
+  // the kernel behind this one (the next call) may be scheduled as soon as SMs free up; it waits for this grid's completion
+  // and, through the plan's sequence word, for the call in front of this grid.  No wait here: the buffer written was last
+  // read two calls ago, and a grid that blocks while resident could starve another rank sharing the GPU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const size_t total = (size_t)n.K * n.half_T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t k = (uint32_t)(i / n.half_T), idx = (uint32_t)(i - (size_t)k * n.half_T);
+    uint32_t c0 = idx, c1 = (uint32_t)n.k_offset + k, c2 = n.call, c3 = kDomainMppi;
 #pragma unroll
-      for (int w = 1; w < kMppiWarps; w++) m = fmin(m, smin[(ss * kMppiWarps + w) * G + gg]);
-      double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int w = 0; w < kMppiWarps; w++)
-#pragma unroll
-        for (int j = 0; j < 5; j++) v[j] += ssum[((ss * kMppiWarps + w) * 5 + j) * G + gg];
-      double *out = a.partials + ((size_t)t * gridDim.x + blockIdx.x) * 6;
-      reinterpret_cast<double2 *>(out)[0] = make_double2(m, v[0]);
-      reinterpret_cast<double2 *>(out)[1] = make_double2(v[1], v[2]);
-      reinterpret_cast<double2 *>(out)[2] = make_double2(v[3], v[4]);
+    for (int r = 0; r < 10; r++) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ n.key0[r], n2 = hi0 ^ c3 ^ n.key1[r];
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
+    float4 z;
+    box_muller_f32(c0, c1, z.x, z.y);
+    box_muller_f32(c2, c3, z.z, z.w);
+    n.zbuf[i] = z;
   }
 }
 
-// One CTA per time step: merge the partials, then (unless merge_only) the control update of
-// mppi.cpp:112-137 for that step, written one slot to the left (the receding-horizon shift).
+// ---- the update as a separate kernel: the NCCL transport of a sharded job and the partials tap -------------------------
+// One CTA per time step: merge the partials, then (unless merge_only) the control update of mppi.cpp:112-137 for that
+// step, written one slot to the left (the receding-horizon shift).
 constexpr int kMppiUpdateThreads = 128;
-
-// merge of the step's partials by one CTA: minimum first, then every partial rescaled once (independent
-// exponentials), plain sums.  The result is valid in thread 0.
-__device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int p_stride, int t_stride, int t, double inv_lambda, double &m,
-                                                 double &S, double &A, double &B, double &DL, double &DR)
-{
-  constexpr int kPer = 4;                                   // partials held in registers per thread (one L2 round trip)
-  __shared__ double red[kMppiUpdateThreads / 32][6];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double inf = __longlong_as_double(0x7FF0000000000000LL);
-  const double *base = partials + (size_t)t * t_stride;
-  double2 c0[kPer], c1[kPer], c2[kPer];
-  m = inf;
-#pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    const int p = threadIdx.x + i * kMppiUpdateThreads;
-    c0[i] = make_double2(inf, 0.0); c1[i] = make_double2(0.0, 0.0); c2[i] = make_double2(0.0, 0.0);
-    if (p < n_partials) {
-      const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
-      c0[i] = c[0]; c1[i] = c[1]; c2[i] = c[2];
-    }
-    m = fmin(m, c0[i].x);
-  }
-  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) m = fmin(m, base[(size_t)p * p_stride]);
-  m = warp_min(m);
-  if (lane == 0) red[warp][0] = m;
-  __syncthreads();
-  m = red[0][0];
-#pragma unroll
-  for (int w = 1; w < kMppiUpdateThreads / 32; w++) m = fmin(m, red[w][0]);
-  S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
-#pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    if (c0[i].x != inf) {
-      const double f = (c0[i].x == m) ? 1.0 : mppi_exp_neg((m - c0[i].x) * inv_lambda);
-      S = fma(c0[i].y, f, S); A = fma(c1[i].x, f, A); B = fma(c1[i].y, f, B);
-    }
-    DL += c2[i].x; DR += c2[i].y;
-  }
-  for (int p = threadIdx.x + kPer * kMppiUpdateThreads; p < n_partials; p += kMppiUpdateThreads) {
-    const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
-    const double2 d0 = c[0], d1 = c[1], d2 = c[2];
-    if (d0.x != inf) {
-      const double f = (d0.x == m) ? 1.0 : mppi_exp_neg((m - d0.x) * inv_lambda);
-      S = fma(d0.y, f, S); A = fma(d1.x, f, A); B = fma(d1.y, f, B);
-    }
-    DL += d2.x; DR += d2.y;
-  }
-  S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
-  __syncthreads();
-  if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kMppiUpdateThreads / 32; w++) {
-      S += red[w][1]; A += red[w][2]; B += red[w][3]; DL += red[w][4]; DR += red[w][5];
-    }
-  }
-}
-
-// the control update of mppi.cpp:112-137 for step t from the fully merged sums (one thread)
-__device__ __forceinline__ void mppi_apply_update(const MppiUpdateArgs &a, int t, double m, double S, double A, double B, double DL, double DR)
-{
-  const int T = a.T;
-  // w_k = exp(-(J_k - min)/lambda) + 1e-8, normalised (mppi.cpp:117-118)
-  const double sumw = S + a.k_total * 1e-8;
-  const double inv = 1.0 / sumw;
-  double nl = a.u_cur[t] + (A + 1e-8 * DL) * inv;           // mppi.cpp:120-121
-  double nr = a.u_cur[T + t] + (B + 1e-8 * DR) * inv;
-  nl = fmin(fmax(nl, -a.umax), a.umax);                     // mppi.cpp:124-125
-  nr = fmin(fmax(nr, -a.umax), a.umax);
-  if (t == 0) {                                             // mppi.cpp:129-131
-    a.out[0] = nl; a.out[1] = nr;
-    if (a.out_seq) {
-      // the host polls this word instead of paying a stream synchronisation for 16 bytes
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.out_seq), "l"(a.seq) : "memory");
-    }
-  }
-  else { a.u_next[t - 1] = nl; a.u_next[T + t - 1] = nr; }  // mppi.cpp:134
-  if (t == T - 1) { a.u_next[T - 1] = a.uinit[0]; a.u_next[2 * T - 1] = a.uinit[1]; }   // mppi.cpp:136-137
-  a.stepstats[2 * t] = m;
-  a.stepstats[2 * t + 1] = sumw;
-}
 
 __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const MppiUpdateArgs a)
 {
@@ -515,98 +1062,14 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
   // the next call's rollout grid may be scheduled now (its prologue overlaps this kernel; it waits before the plan)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double m, S, A, B, DL, DR;
-  mppi_block_merge(a.partials, a.n_partials, a.p_stride, a.t_stride, t, a.inv_lambda, m, S, A, B, DL, DR);
+  mppi_block_merge<kMppiUpdateThreads, false>(a.partials, a.n_partials, a.p_stride, a.t_stride, t, a.inv_lambda, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
   if (a.merge_only) {
     double *o = a.merged + (size_t)t * 6;
     o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
     return;
   }
-  mppi_apply_update(a, t, m, S, A, B, DL, DR);
-}
-
-// ---- sharded rollouts: merge + exchange + update in ONE kernel over NVLink peer memory ----------------
-// Every rank owns an exchange area [2 call parities][nranks][T][12] of 8-byte words; peer[j] is rank j's area mapped
-// into this process (CUDA IPC).  CTA t merges this rank's CTA partials for step t and sends the 48-byte result to every
-// rank (its own included: one code path) in the low-latency style of NCCL's LL protocol: each 8-byte word carries 4
-// bytes of payload and the 32-bit call id, and 8-byte stores are single NVLink transactions, so a word whose upper half
-// shows the current call id IS its payload - no fence, no separate flag, one NVLink write latency.  The CTA then spins
-// on the 12 x nranks words of its own area, and thread 0 folds the nranks results in rank order (identical on every
-// rank, so the plan stays replicated without a broadcast) and applies the update.  No NCCL call, no extra launch.
-// A slot of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's
-// data of call c + 1, which was sent after this rank finished reading call c: two parities are enough.
-constexpr int kMppiMaxRanks = 64;
-constexpr int kMppiXchgWords = 12;                // 6 doubles = 12 payload halves
-
-struct MppiXchgArgs
-{
-  unsigned long long *peer[kMppiMaxRanks];        // rank j's area [2][nranks][T][12]
-  int rank, nranks, parity;                       // parity = call number & 1
-  uint32_t call_id;                               // call number folded into 1 .. 2^32 - 1: never 0 (the areas start zeroed)
-};
-
-__global__ void __launch_bounds__(kMppiUpdateThreads) mppi_exchange_update_kernel(const MppiUpdateArgs a, const __grid_constant__ MppiXchgArgs x)
-{
-  __shared__ uint32_t mine[kMppiXchgWords];
-  __shared__ uint32_t all[kMppiMaxRanks][kMppiXchgWords];
-  const int t = blockIdx.x, T = a.T;
-  const int par = x.parity;
-  asm volatile("griddepcontrol.wait;" ::: "memory");                 // programmatic dependent launch, as in mppi_update_kernel
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  double m, S, A, B, DL, DR;
-  mppi_block_merge(a.partials, a.n_partials, a.p_stride, a.t_stride, t, a.inv_lambda, m, S, A, B, DL, DR);
-  if (threadIdx.x == 0) {
-    const double v[6] = {m, S, A, B, DL, DR};
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      mine[2 * i] = (uint32_t)__double2loint(v[i]);
-      mine[2 * i + 1] = (uint32_t)__double2hiint(v[i]);
-    }
-  }
-  __syncthreads();
-  const int n_words = x.nranks * kMppiXchgWords;
-  for (int i = threadIdx.x; i < n_words; i += kMppiUpdateThreads) {
-    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
-    // word w of this rank's slot in rank r's area
-    unsigned long long *dst = x.peer[r] + (((size_t)par * x.nranks + x.rank) * T + t) * kMppiXchgWords + w;
-    const unsigned long long packed = ((unsigned long long)x.call_id << 32) | mine[w];
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(packed) : "memory");
-  }
-  for (int i = threadIdx.x; i < n_words; i += kMppiUpdateThreads) {
-    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
-    const unsigned long long *src = x.peer[x.rank] + (((size_t)par * x.nranks + r) * T + t) * kMppiXchgWords + w;
-    unsigned long long got;
-    unsigned polls = 0;
-    do {
-      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
-      if (++polls == (1u << 27)) __trap();          // about a minute without the peer's word: fail loudly, not silently
-    } while ((uint32_t)(got >> 32) != x.call_id);
-    all[r][w] = (uint32_t)got;
-  }
-  __syncthreads();
-  // fold the nranks results in rank order (identical on every rank).  The rescale factors are independent of one
-  // another: thread r computes rank r's (one exponential each, side by side), thread 0 then runs the ordered sums -
-  // the same operations in the same order as a serial fold, without nranks exponentials back to back
-  __shared__ double fac[kMppiMaxRanks];
-  const double inf = __longlong_as_double(0x7FF0000000000000LL);
-  auto val = [&](int r, int i) { return __hiloint2double((int)all[r][2 * i + 1], (int)all[r][2 * i]); };
-  m = inf;
-  for (int r = 0; r < x.nranks; r++) m = fmin(m, val(r, 0));
-  if ((int)threadIdx.x < x.nranks) {
-    const double mr = val((int)threadIdx.x, 0);
-    fac[threadIdx.x] = (mr == inf) ? 0.0 : (mr == m) ? 1.0 : mppi_exp_neg((m - mr) * a.inv_lambda);
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  S = A = B = DL = DR = 0.0;
-  for (int r = 0; r < x.nranks; r++) {
-    if (val(r, 0) != inf) {
-      const double f = fac[r];
-      S = fma(val(r, 1), f, S); A = fma(val(r, 2), f, A); B = fma(val(r, 3), f, B);
-    }
-    DL += val(r, 4); DR += val(r, 5);
-  }
-  mppi_apply_update(a, t, m, S, A, B, DL, DR);
+  mppi_apply_update(a, a.u_cur, t, m, S, A, B, DL, DR);
 }
 
 // parity tap: the normalised weights the reference materialises at mppi.cpp:117-118

@@ -4,6 +4,7 @@ Tolerances (BASELINE.json north_star): 1e-5 relative on trajectory states, weigh
 controls.  The fp64 kernels land orders of magnitude inside that; the asserts below use the
 contract tolerance for the headline quantities and tighter ones where a regression would hide.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -140,6 +141,66 @@ def test_config_c2_full_size(gpu_pkg):
         pose = orc.unicycle_step(pose, co[0], co[1], dt)
 
 
+def test_box_muller_every_radius_bit_exact(gpu_pkg):
+    """The perturbation generator's Box-Muller stage for ALL 2^23 possible first words (every radius: ln by polynomial, square
+    root by SFU seed + one fused Newton step) and four second words (one per quadrant): bit for bit the oracle's fmaf / sqrtf."""
+    lib = gpu_pkg.load_library()
+    L = orc.oracle_lib()
+    L.orc_box_muller_range.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.orc_box_muller_range.restype = None
+    n = 1 << 23
+    for rb in (0x12345678, 0x6badf00d, 0x9e3779b9, 0xfedcba98):
+        zg, zo = np.empty(2 * n, dtype=np.float32), np.empty(2 * n, dtype=np.float32)
+        assert lib.b2n_test_box_muller(0, n, rb, zg.ctypes.data_as(C.c_void_p)) == 0
+        L.orc_box_muller_range(0, n, rb, zo.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(zg.view(np.uint32), zo.view(np.uint32)), rb
+    # second word: 2^16 angles spread over the range, a few radii
+    rbs = np.arange(0, 1 << 32, 65537, dtype=np.uint64).astype(np.uint32)
+    zg, zo = np.empty(2, dtype=np.float32), np.empty(2, dtype=np.float32)
+    for rb in rbs[::257]:
+        assert lib.b2n_test_box_muller(4242, 1, int(rb), zg.ctypes.data_as(C.c_void_p)) == 0
+        L.orc_box_muller_range(4242, 1, int(rb), zo.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(zg.view(np.uint32), zo.view(np.uint32)), rb
+
+
+@pytest.mark.parametrize("K,ring,calls", [(16384, 1, 4), (2048, 3, 5), (16384, 3, 3)])
+def test_production_variant_matches_oracle_at_c2(gpu_pkg, K, ring, calls):
+    """BASELINE configs[1] on the instantiation the bench times: capture OFF, so newControls() runs the FAST
+    (S = 4, G = 16) rollout variant with the fused tail.  Controls, plan and the fp32 state tensor against the
+    oracle over receding-horizon calls; K = 2048 is the 8-GPU share of C2, ring = 3 the bench's state ring."""
+    hor, dt = 0.64, 0.01
+    o = orc.OracleMppi(hor, dt, K)
+    gpu = make_gpu(gpu_pkg, hor, dt, K)
+    if ring > 1:
+        gpu.setStateRing(ring)
+    gpu.seed(42)
+    o.noise_philox(42)
+    o.setWaypoint(1.0, 0.0, 1.5707)
+    gpu.setWaypoint(gpu_pkg.Pose(theta=1.5707, x=1.0, y=0.0))
+    pose = (0.0, 0.0, 0.0)
+    for c in range(calls):
+        v = gpu.newControls(gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        assert gpu.lastVariant() == "fast", "the production variant did not run"
+        co = o.newControls(*pose)
+        g = o.get()
+        assert rel_err([v.ul, v.ur], co, 1e-3) < RTOL, (c, v, co)
+        assert rel_err(gpu.plan(), g["plan"], 1e-3) < RTOL
+        s, so = gpu.states(), g["states"]
+        assert np.max(np.abs(s - so) / np.maximum(np.abs(so), 1e-2)) < RTOL
+        assert np.max(np.abs(s - so.astype(np.float32))) <= 2.4e-7 * np.max(np.abs(so))
+        # the merged per-step sums the update consumed (min J, sum e, sum e*du, sum du) against the oracle's J and du
+        p = gpu.partials()
+        Jo = g["J"]
+        m = Jo.min(axis=1)
+        e = np.exp(-(Jo - m[:, None]) / orc.SHIPPED["lambda_"])
+        assert rel_err(p[:, 0], m, 1e-6) < 1e-11
+        assert rel_err(p[:, 1], e.sum(axis=1), 1e-300) < 1e-6
+        assert np.allclose(p[:, 2], (e * g["du"][:, :, 0].T).sum(axis=1), rtol=1e-5, atol=1e-9)
+        assert np.allclose(p[:, 3], (e * g["du"][:, :, 1].T).sum(axis=1), rtol=1e-5, atol=1e-9)
+        assert np.allclose(p[:, 4], g["du"][:, :, 0].sum(axis=0), rtol=1e-5, atol=1e-3)
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
+
+
 def test_config_c4_shard_size_with_obstacles(gpu_pkg):
     """BASELINE config 4 per-GPU shard (8192 of 65536 rollouts, T = 128) with the obstacle term on."""
     hor, dt, K = 1.28, 0.01, 8192
@@ -195,6 +256,50 @@ def test_shards_compose_to_the_full_job(gpu_pkg):
         assert np.allclose(ph[0][:, j] * f[0] + ph[1][:, j] * f[1], pf[:, j], rtol=1e-9, atol=1e-12)
     for j in (4, 5):
         assert np.allclose(ph[0][:, j] + ph[1][:, j], pf[:, j], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("nranks,K,T_cfg,ahead", [(2, 16384, (0.64, 0.01), False), (2, 2048, (0.64, 0.01), True), (4, 2048, (0.64, 0.01), False),
+                                                  (2, 4096, (1.28, 0.01), False), (8, 1024, (0.32, 0.01), False)])
+def test_sharded_exchange_on_one_gpu_matches_the_unsharded_oracle(gpu_pkg, monkeypatch, nranks, K, T_cfg, ahead):
+    """The sharded path - every rank's merger CTAs exchange their step's [6] sums over peer memory inside the call's one
+    kernel and apply the identical update - with the ranks as handles of THIS process sharing ONE GPU (separate streams):
+    the production (FAST) instantiation against the UNSHARDED oracle on the whole job, and the plan replicated bit for bit
+    on every rank.  Merger CTAs wait for the other ranks' words while resident, so on a shared GPU every rank's grid must
+    be able to start: the sizes keep the merger CTAs of all ranks well inside the GPU, and the kernels that draw the next
+    call's variates behind a call (they queue more CTAs than the GPU holds) are switched off except in the smallest case.
+    With one GPU per rank - the way the path is deployed - there is no such coupling."""
+    monkeypatch.setenv("B2N_MPPI_NOISE_AHEAD", "1" if ahead else "0")
+    hor, dt = T_cfg
+    Kr = K // nranks
+    o = orc.OracleMppi(hor, dt, K)
+    ranks = [make_gpu(gpu_pkg, hor, dt, Kr, rollout_offset=r * Kr, rollouts_total=K) for r in range(nranks)]
+    for m in ranks:
+        m.p2pExport(nranks)
+    areas = [m.p2pArea() for m in ranks]
+    for r, m in enumerate(ranks):
+        m.p2pInitLocal(r, nranks, areas)
+        m.seed(42)
+        m.setWaypoint(gpu_pkg.Pose(theta=1.5707, x=1.0, y=0.0))
+    o.noise_philox(42)
+    o.setWaypoint(1.0, 0.0, 1.5707)
+    pose = (0.0, 0.0, 0.0)
+    for c in range(4):
+        P = gpu_pkg.Pose(theta=pose[2], x=pose[0], y=pose[1])
+        for m in ranks:
+            m.enqueue(P)
+        vs = [m.wait() for m in ranks]
+        assert all(m.lastVariant() == "fast" for m in ranks)
+        co = o.newControls(*pose)
+        plans = [m.plan() for m in ranks]
+        for v, p in zip(vs, plans):
+            assert rel_err([v.ul, v.ur], co, 1e-3) < RTOL, (c, v, co)
+            assert rel_err(p, o.get()["plan"], 1e-3) < RTOL
+            assert (v.ul, v.ur) == (vs[0].ul, vs[0].ur) and np.array_equal(p, plans[0])
+        so = o.get()["states"]
+        for r, m in enumerate(ranks):
+            s = m.states()
+            assert np.max(np.abs(s - so[r * Kr:(r + 1) * Kr]) / np.maximum(np.abs(so[r * Kr:(r + 1) * Kr]), 1e-2)) < RTOL
+        pose = orc.unicycle_step(pose, co[0], co[1], dt)
 
 
 def test_zero_variance_leaves_the_plan_alone(gpu_pkg):
@@ -255,7 +360,9 @@ def test_state_ring_and_launch_count(gpu_pkg):
         gpu.newControls(gpu_pkg.Pose())
         if i == 0:
             first = gpu.states().copy()
-    assert gpu.launchCount() - n0 == 8                   # rollout + update per call
+    # ONE kernel per call (rollouts, merge tree, update) + the kernel that draws the next call's variates behind it; the
+    # first call also draws its own
+    assert gpu.launchCount() - n0 == 9
     assert not np.array_equal(first, gpu.states())
 
 

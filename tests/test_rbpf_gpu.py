@@ -210,6 +210,36 @@ def test_config_c3_properties_at_full_size(gpu_pkg):
         assert len(a.occOrder(k)) == int(np.sum(g["state"] == 1))
 
 
+def test_config_c3_full_size_against_the_oracle(gpu_pkg):
+    """BASELINE configs[2] at FULL size against the CPU oracle (not against itself): 4096 particles, 360 beams, 200x200 map,
+    two scans on the same Philox streams.  Weights and poses at 1e-9, N_eff / resample flag / ancestors bit-exact, three full
+    maps (log-odds, distance field, cell classes, occupied-set iteration order) bit-exact, exported map equal.  The oracle
+    needs about 15 s per scan at this size."""
+    N, scans = 4096, 2
+    poses, twists = orc.circle_path(scans)
+    rng = np.random.default_rng(4)
+    kw = dict(num_particles=N, init_pose=tuple(poses[0]), motion_noise=(2e-3, 1e-3, 1e-3))
+    f = make_gpu(gpu_pkg, **kw)
+    o = orc.OraclePf(**kw)
+    f.seed(1234)
+    o.noise_philox(1234)
+    for i in range(scans):
+        scan = orc.room_scan(poses[i + 1], rng=rng)
+        slam_gpu(gpu_pkg, f, scan, twists[i], poses[i + 1], poses[i])
+        o.slam(scan, twists[i], poses[i + 1], poses[i])
+        st = o.state()
+        assert rel(f.weights(), st["weights"]) < 1e-9, i
+        assert np.max(np.abs(f.poses()[0] - st["poses"])) < 1e-9, i
+        ng, rg, ag = f.resampleInfo()
+        no, ro, ao = o.resample_info()
+        assert (ng, rg) == (no, ro) and np.array_equal(ag, ao), i
+    for k in (0, 2049, N - 1):
+        assert_grid_equal(f.grid(k), o.grid(k))
+        assert np.array_equal(f.occOrder(k), o.occ_order(k))
+    assert np.array_equal(f.newMap(), o.new_map())
+    assert np.max(np.abs(np.subtract(f.getRobotState().displacement(), o.robot_state()))) < 1e-9
+
+
 def test_error_behaviour(gpu_pkg):
     poses, twists = orc.circle_path(1)
     f = make_gpu(gpu_pkg, num_particles=4, xmin=-2.0, xmax=2.0, ymin=-2.0, ymax=2.0)

@@ -16,7 +16,7 @@ params = sys.argv[4] if len(sys.argv) > 4 else "shipped"
 pkg = _pkg.load()
 orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED if params == "shipped" else orc.MILD
-shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8), (4, 16, 7)]
+shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8), (4, 16, 10), (4, 16, 20), (4, 32, 20)]
 if os.environ.get("PROBE_SHAPES"):
     shapes = [tuple(int(v) for v in x.split(",")) for x in os.environ["PROBE_SHAPES"].split(";")]
 for shape in shapes:
@@ -40,12 +40,11 @@ for shape in shapes:
         m.enqueue(pose)
     m.wait()
     el = (time.perf_counter() - t0) / n
-    m.setKernelTiming(True)
+    t0 = time.perf_counter()
     for _ in range(n):
-        m.enqueue(pose)
-    m.wait()
-    kms, kn = m.kernelTime()
+        m.newControls(pose)
+    sync = (time.perf_counter() - t0) / n
     kms = m.timeRollout(pose, n)
-    print("K=%d T=%d %s shape S=%d G=%d NW=%d: %.2f us/call (%.3e traj-steps/s), rollout kernel %.2f us (back to back)"
-          % (K, T, params, S, G, NW, el * 1e6, K * T / el, kms * 1e3), flush=True)
+    print("K=%d T=%d %s shape S=%d G=%d NW=%d: %.2f us/call pipelined (%.3e traj-steps/s), %.2f us/call synchronous, rollout phase %.2f us (back to back), variant %s"
+          % (K, T, params, S, G, NW, el * 1e6, K * T / el, sync * 1e6, kms * 1e3, m.lastVariant()), flush=True)
     del m
