@@ -42,14 +42,15 @@ ALGO_BYTES_PER_TRAJ_STEP = 12     # fp32 (x, y, theta) written once (SURVEY.md 8
 WAYPOINT = (1.0, 0.0, 1.5707)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange="p2p"):
     return {
         "workload": "MPPI K=16384 T=64 diff-drive, quadratic waypoint cost (BASELINE configs[1]), shipped cost params",
         "rollouts_per_gpu": K_ROLLOUTS, "rollouts_total": K_ROLLOUTS * n_gpus, "horizon_steps": 64,
         "noise": "Philox4x32-10 counter-based + binary32 Box-Muller, seed 42",
         "l2": "state tensor written round-robin into %d buffers (%.0f MB) > 126 MB L2" % (STATE_RING, STATE_RING * K_ROLLOUTS * 64 * 12 / 1e6),
         "clock_ramp": "%d untimed pipelined calls (about 0.5 s) before the W warm-up steps (--no-ramp: none)" % RAMP_CALLS,
-        "sharding": "rollouts; [T][6] partial exchanged inside the update kernel over NVLink peer memory (--exchange nccl: ncclAllGather)" if n_gpus > 1 else "none",
+        "sharding": "rollouts; every step's [6] sums exchanged by the call's merger CTAs over NVLink peer memory (--exchange nccl: ncclAllGather)" if n_gpus > 1 else "none",
+        "exchange": exchange if n_gpus > 1 else "none",
     }
 
 
@@ -179,33 +180,7 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
     particles whose ancestor lives on another GPU migrate (ncclSend/ncclRecv)."""
     poses, twists, scans = rbpf_inputs(n_scans + warmup)
     q = pkg.synthetic.pf_params(num_particles=RBPF_N, init_pose=tuple(poses[0]), motion_noise=RBPF_MOTION_NOISE)
-    if world > 1:
-        f = pkg.bmapping.make_filter(q, particle_offset=rank * RBPF_N, particles_total=world * RBPF_N, device=local)
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        if exchange == "p2p":
-            mine = torch.frombuffer(bytearray(f.p2pExport()), dtype=torch.uint8).cuda()
-            hs = [torch.zeros(640, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            dist.all_gather(hs, mine)
-            ok = torch.ones(1, dtype=torch.int32, device="cuda")
-            try:
-                f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
-            except pkg.B2NError:
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:                 # some rank cannot map its peers: everyone migrates with ncclSend/ncclRecv
-                exchange = "nccl"
-                f.close()
-                f = pkg.bmapping.make_filter(q, particle_offset=rank * RBPF_N, particles_total=world * RBPF_N, device=local)
-                if rank == 0:
-                    uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-                dist.broadcast(uid, 0)
-                f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
-    else:
-        f = pkg.bmapping.make_filter(q, device=local)
+    f, exchange = make_filter(pkg, torch, dist, q, RBPF_N, rank, world, local, exchange)
     f.seed(1)
     f.setKernelTiming(True)
     ms = [0.0, 0.0, 0.0]
@@ -307,7 +282,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus, args.exchange),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -317,6 +292,258 @@ def run_reference_arm(args):
     if not args.no_rbpf:
         line["rbpf"] = rbpf_cpu(kind)
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------------------- handle factories ------
+def make_mppi(pkg, torch, dist, horizon, dt, k_per_rank, rank, world, local, exchange):
+    """controller::MPPI on this rank's slice of the rollouts; at world > 1 wired for the exchange (peer memory, or NCCL
+    when a rank cannot map its peers).  Returns (handle, exchange actually used)."""
+    prm = pkg.synthetic.SHIPPED          # inputs only; the CPU checkers are imported by the cpu_baseline / parity legs alone
+
+    def create():
+        return pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
+                        prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], horizon, dt, k_per_rank,
+                        rollout_offset=rank * k_per_rank, rollouts_total=world * k_per_rank, device=local)
+
+    def nccl_wire(m):
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        m.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+    m = create()
+    if world == 1:
+        return m, "none"
+    if exchange == "p2p":
+        # exchange inside the call's kernel over NVLink peer memory: gather every rank's CUDA IPC handle; if any rank cannot
+        # map its peers (no peer access, GPUs hidden from each other) every rank falls back to ncclAllGather
+        mine = torch.frombuffer(bytearray(m.p2pExport(world)), dtype=torch.uint8).cuda()
+        hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(hs, mine)
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            m.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+        except pkg.B2NError:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            return m, "p2p"
+        m.close()
+        m = create()
+    nccl_wire(m)
+    return m, "nccl"
+
+
+def make_filter(pkg, torch, dist, q, n_per_rank, rank, world, local, exchange):
+    """bmapping::ParticleFilter on this rank's slice of the particles (weights allgather + migration by peer-memory copies,
+    or ncclSend / ncclRecv when a rank cannot map its peers).  Returns (filter, exchange actually used)."""
+    if world == 1:
+        return pkg.bmapping.make_filter(q, device=local), "none"
+
+    def create():
+        f = pkg.bmapping.make_filter(q, particle_offset=rank * n_per_rank, particles_total=world * n_per_rank, device=local)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        f.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        return f
+
+    f = create()
+    if exchange != "p2p":
+        return f, "nccl"
+    mine = torch.frombuffer(bytearray(f.p2pExport()), dtype=torch.uint8).cuda()
+    hs = [torch.zeros(640, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(hs, mine)
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    try:
+        f.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
+    except pkg.B2NError:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
+        return f, "p2p"
+    f.close()                                       # some rank cannot map its peers: everyone migrates with ncclSend/ncclRecv
+    return create(), "nccl"
+
+
+# --------------------------------------------------------------------------- parity check --------
+def mppi_parity_check(pkg, torch, dist, rank, world, local, exchange, calls=3):
+    """A fresh handle of the benched configuration (sharded exactly like the timed one), `calls` receding-horizon calls, against
+    the UNSHARDED CPU oracle on all world x K rollouts (rank 0; the oracle is the checker here, as in the tests): the bench line
+    carries its own evidence that the kernels it timed compute the reference's controls."""
+    syn = pkg.synthetic
+    m, _ = make_mppi(pkg, torch, dist, HORIZON, DT, K_ROLLOUTS, rank, world, local, exchange)
+    m.seed(42)
+    m.setWaypoint(pkg.Pose(theta=WAYPOINT[2], x=WAYPOINT[0], y=WAYPOINT[1]))
+    o = None
+    if rank == 0:
+        import _oracle as orc
+        o = orc.OracleMppi(HORIZON, DT, K_ROLLOUTS * world)
+        o.noise_philox(42)
+        o.setWaypoint(*WAYPOINT)
+    pose, worst_c, worst_p, worst_s = (0.0, 0.0, 0.0), 0.0, 0.0, 0.0
+    import numpy as np
+    for _ in range(calls):
+        v = m.newControls(pkg.Pose(theta=pose[2], x=pose[0], y=pose[1]))
+        variant = m.lastVariant()
+        if rank == 0:
+            c = o.newControls(*pose)
+            g = o.get()
+            worst_c = max(worst_c, max(abs(v.ul - c[0]), abs(v.ur - c[1])) / max(1e-3, abs(c[0]), abs(c[1])))
+            worst_p = max(worst_p, float(np.max(np.abs(m.plan() - g["plan"]) / np.maximum(np.abs(g["plan"]), 1e-3))))
+            so = g["states"][:K_ROLLOUTS]
+            worst_s = max(worst_s, float(np.max(np.abs(m.states() - so) / np.maximum(np.abs(so), 1e-2))))
+        pose = syn.unicycle_step(pose, v.ul, v.ur, DT)      # the GPU's controls are identical on every rank: so are the poses
+    m.close()
+    return {"controls_rel_err": worst_c, "plan_rel_err": worst_p, "states_rel_err": worst_s, "calls": calls, "kernel_variant": variant,
+            "against": "unsharded CPU oracle on %d rollouts, same Philox streams" % (K_ROLLOUTS * world), "tolerance": 1e-5}
+
+
+# ------------------------------------------------------------------------------- C4 leg ----------
+C4_K, C4_HORIZON, C4_DT = 65536, 1.28, 0.01                 # BASELINE configs[3]: K = 65536, T = 128, obstacle term on
+
+
+def c4_obstacle_field():
+    """distance (m) to the nearest obstacle of the synthetic room's box, 200 x 200 cells of 5 cm over [-5, 5]^2"""
+    import numpy as np
+    c = -5.0 + 0.05 * (np.arange(200) + 0.5)
+    X, Y = np.meshgrid(c, c, indexing="ij")
+    dx = np.maximum(np.maximum(0.45 - X, X - 0.85), 0.0)       # a box ahead of the start pose, inside the horizon's reach
+    dy = np.maximum(np.maximum(-0.25 - Y, Y - 0.25), 0.0)
+    return np.hypot(dx, dy).astype(np.float32)
+
+
+def c4_leg(pkg, torch, dist, rank, world, local, exchange, steps):
+    """BASELINE configs[3]: MPPI K = 65536, T = 128 with the occupancy-grid obstacle term, the rollouts SPLIT over the GPUs
+    (strong scaling).  Per-call time pipelined (device) and synchronous (host pose in, host controls out); at N > 1 rank 0
+    also times the whole job on its own GPU in the same run, so the speed-up is measured on one box."""
+    def timed(m, n):
+        stream = torch.cuda.Stream(device=local)
+        m.setStream(stream.cuda_stream)
+        m.setStateRing(2)
+        m.seed(42)
+        m.setObstacleField(c4_obstacle_field(), -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+        m.setWaypoint(pkg.Pose(theta=0.0, x=1.5, y=0.0))
+        pose = pkg.Pose(theta=0.0, x=0.0, y=0.0)
+        for _ in range(20):
+            m.newControls(pose)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(n):
+            m.enqueue(pose)
+        e1.record(stream)
+        m.wait()
+        torch.cuda.synchronize()
+        dev_us = 1e3 * e0.elapsed_time(e1) / n
+        t0 = time.perf_counter()
+        for _ in range(n):
+            v = m.newControls(pose)
+        sync_us = 1e6 * (time.perf_counter() - t0) / n
+        return dev_us, sync_us, m.lastVariant(), (v.ul, v.ur)
+
+    k_rank = C4_K // world
+    m, used = make_mppi(pkg, torch, dist, C4_HORIZON, C4_DT, k_rank, rank, world, local, exchange)
+    if world > 1:
+        dist.barrier()
+    dev_us, sync_us, variant, ctl = timed(m, steps)
+    m.close()
+    if world > 1:
+        t = torch.tensor([dev_us, sync_us], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_us, sync_us = float(t[0]), float(t[1])
+    out = {"workload": "MPPI K=65536 T=128 with occupancy-grid obstacle term (BASELINE configs[3]), rollouts split over the GPUs (strong scaling)",
+           "n_gpus": world, "rollouts_per_gpu": k_rank, "exchange": used, "kernel_variant": variant,
+           "us_per_call": dev_us, "us_per_call_synchronous": sync_us,
+           "trajectory_steps_per_sec": C4_K * 128 / (dev_us * 1e-6), "last_controls": list(ctl)}
+    if world > 1:
+        if rank == 0:
+            m1, _ = make_mppi(pkg, torch, None, C4_HORIZON, C4_DT, C4_K, 0, 1, local, "none")
+            d1, s1, _, _ = timed(m1, max(20, steps // 4))
+            m1.close()
+            out["one_gpu_same_box"] = {"us_per_call": d1, "us_per_call_synchronous": s1}
+            out["speedup_vs_one_gpu"] = d1 / dev_us
+            out["speedup_vs_one_gpu_synchronous"] = s1 / sync_us
+        dist.barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------- C5 leg ----------
+def c5_leg(pkg, torch, dist, rank, world, local, exchange, ticks):
+    """BASELINE configs[4]: RBPF (4096 particles per GPU: 32768 on eight) + MPPI K = 16384 (split over the GPUs) in closed loop
+    on a synthetic trajectory: control at 50 Hz, lidar at 5 Hz.  The loop is the reference's nodes fused
+    (mppi_waypoints_node.cpp:231-282, turtle_mapping_node.cpp:451-494): waypoint bookkeeping, newControls() on the pose estimate,
+    wheelsToTwist, the simulated robot (DiffDrive::feedforward as fake_diff_encoders drives it), odometers on its encoders,
+    SLAM() + getRobotState() on every scan.  Every rank runs the same host loop on the same seeds, so scans and poses agree
+    without communication; the filter's answer is the best particle of all ranks."""
+    import numpy as np
+    syn = pkg.synthetic
+    prm = syn.SHIPPED
+    dt, hor, scan_every = 0.02, 1.28, 10              # 50 Hz control, T = 64 at dt = 0.02, a scan every 10th tick
+    start = (0.0, 0.0, 0.0)
+    q = syn.pf_params(num_particles=RBPF_N, init_pose=start, motion_noise=RBPF_MOTION_NOISE)
+    f, used_f = make_filter(pkg, torch, dist, q, RBPF_N, rank, world, local, exchange)
+    f.seed(1)
+    m, used_m = make_mppi(pkg, torch, dist, hor, dt, K_ROLLOUTS // world, rank, world, local, exchange)
+    m.seed(2)
+    sw = syn.WaypointSwitch([0.8, 1.05, 0.4, -0.25, 0.0], [0.0, 0.76, 1.23, 0.76, 0.0], [0.0, 1.5707, 2.3562, -2.3562, -1.5707], 0.08)
+    wx, wy, wth = sw.current()
+    m.setWaypoint(pkg.Pose(theta=wth, x=wx, y=wy))
+    robot, odo, pf_drive = (syn.DiffDrive(start, prm["wheel_base"], prm["wheel_radius"]) for _ in range(3))
+    rng = np.random.default_rng(0)
+    # the first scan builds the map before the robot moves
+    f.SLAM(syn.room_scan(start, rng=rng), pkg.Twist2D(0.0, 0.0, 0.0), pkg.Pose(*start), pkg.Pose(*start))
+    est, prev_odom = start, start
+    t_mppi, t_slam, reached, resampled = [], [], 0, 0
+    for k in range(ticks):
+        nw = sw.update(est[1], est[2])
+        if nw is not None:
+            reached += 1
+            m.setWaypoint(pkg.Pose(theta=nw[2], x=nw[0], y=nw[1]))
+        t0 = time.perf_counter()
+        v = m.newControls(pkg.Pose(theta=est[0], x=est[1], y=est[2]))
+        t_mppi.append(time.perf_counter() - t0)
+        w, vx, _ = robot.wheelsToTwist(v.ul, v.ur)
+        robot.feedforward(w * dt, vx * dt)
+        left, right = robot.getEncoders()
+        odo.updateOdometry(left, right)
+        est = odo.pose()
+        if (k + 1) % scan_every:
+            continue
+        pf_drive.updateOdometry(left, right)
+        cur_odom = pf_drive.pose()
+        twist = pf_drive.wheelsToTwist(*pf_drive.wheelVelocities())
+        scan = syn.room_scan(robot.pose(), rng=rng)
+        t0 = time.perf_counter()
+        f.SLAM(scan, pkg.Twist2D(*twist), pkg.Pose(*cur_odom), pkg.Pose(*prev_odom))
+        est = f.getRobotState().displacement()
+        t_slam.append(time.perf_counter() - t0)
+        resampled += f.resampleInfo()[1]
+        prev_odom = cur_odom
+        odo = syn.DiffDrive(est, prm["wheel_base"], prm["wheel_radius"])       # the odometer restarts from the filter's pose,
+        odo.left_curr, odo.right_curr = left, right                            #   on the current encoder angles
+    true = robot.pose()
+    err = float(np.hypot(est[1] - true[1], est[2] - true[2]))
+    stats = np.array([np.mean(t_mppi), np.percentile(t_mppi, 99), np.max(t_mppi), np.mean(t_slam), np.max(t_slam)])
+    if world > 1:
+        t = torch.from_numpy(stats).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stats = t.cpu().numpy()
+    f.close()
+    m.close()
+    return {"workload": "closed loop RBPF + MPPI at 50 Hz control / 5 Hz lidar on a synthetic trajectory (BASELINE configs[4])",
+            "n_gpus": world, "particles_total": RBPF_N * world, "particles_per_gpu": RBPF_N, "rollouts_total": K_ROLLOUTS,
+            "rollouts_per_gpu": K_ROLLOUTS // world, "horizon_steps": m.steps, "ticks": ticks, "scans": len(t_slam),
+            "exchange": {"mppi": used_m, "rbpf": used_f},
+            "plant": "rigid2d::DiffDrive feedforward / updateOdometry restated in numpy (pinned against the compiled reference by tests/test_host_logic.py)",
+            "mppi_ms_per_tick": {"mean": 1e3 * stats[0], "p99": 1e3 * stats[1], "max": 1e3 * stats[2], "budget": 1e3 * dt},
+            "slam_ms_per_scan": {"mean": 1e3 * stats[3], "max": 1e3 * stats[4], "budget": 1e3 * dt * scan_every,
+                                 "includes": "SLAM() + getRobotState() (at N > 1 the best particle of all ranks, read over peer memory)"},
+            "meets_50hz_budget": bool(1e3 * stats[2] < 1e3 * dt and 1e3 * stats[4] < 1e3 * dt * scan_every),
+            "waypoints_reached": reached, "scans_that_resampled": int(resampled), "final_position_error_m": err}
 
 
 # ------------------------------------------------------------------------------ our arm ----------
@@ -341,39 +568,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
 
-    prm = pkg.synthetic.SHIPPED          # inputs only; the CPU checkers are imported by the cpu_baseline leg alone
-    mppi = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
-                    prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], HORIZON, DT, K_ROLLOUTS,
-                    rollout_offset=rank * K_ROLLOUTS, rollouts_total=world * K_ROLLOUTS, device=local)
+    requested_exchange = args.exchange
+    mppi, args.exchange = make_mppi(pkg, torch, dist, HORIZON, DT, K_ROLLOUTS, rank, world, local, args.exchange)
     T = mppi.steps
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        mppi.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        if args.exchange == "p2p":
-            # exchange inside the update kernel over NVLink peer memory: gather every rank's CUDA IPC handle; if any
-            # rank cannot map its peers (no peer access, GPUs hidden from each other) every rank stays on ncclAllGather
-            mine = torch.frombuffer(bytearray(mppi.p2pExport(world)), dtype=torch.uint8).cuda()
-            hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            dist.all_gather(hs, mine)
-            ok = torch.ones(1, dtype=torch.int32, device="cuda")
-            try:
-                mppi.p2pInit(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in hs))
-            except pkg.B2NError:
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                args.exchange = "nccl"
-                mppi.close()
-                mppi = pkg.MPPI(pkg.CartModel(prm["wheel_radius"], prm["wheel_base"]), pkg.LossFunc(prm["Q"], prm["R"], prm["P1"]),
-                                prm["lambda_"], prm["max_wheel_vel"], prm["ul_var"], prm["ur_var"], HORIZON, DT, K_ROLLOUTS,
-                                rollout_offset=rank * K_ROLLOUTS, rollouts_total=world * K_ROLLOUTS, device=local)
-                if rank == 0:
-                    uid.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-                dist.broadcast(uid, 0)
-                mppi.commInit(rank, world, bytes(uid.cpu().numpy().tobytes()))
     # the handle launches on THIS stream and the timing events are recorded on it (torch's current stream is the
     # legacy default stream, handle 0, which b2n_mppi_set_stream reads as "use your own": events there would bracket
     # nothing but the host's enqueue loop)
@@ -463,7 +660,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(workload_config(world), exchange=(args.exchange if world > 1 else "none")), "clocks": clocks,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, requested_exchange), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24,
                     "d2h_bytes_per_step": 16,
                     "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the update kernel into mapped pinned memory"},
@@ -477,15 +674,28 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_oracle_port()
-    rbpf = None
+    mppi.close()
+    parity = None
+    if not args.no_parity:
+        parity = mppi_parity_check(pkg, torch, dist if world > 1 else None, rank, world, local, args.exchange)
+    rbpf = c4 = c5 = None
     if not args.no_rbpf:
-        mppi.close()
         rbpf = rbpf_gpu_leg(pkg, torch, args.rbpf_scans, 3, rank, world, local, dist if world > 1 else None, args.exchange)
+    if not args.no_c4:
+        c4 = c4_leg(pkg, torch, dist if world > 1 else None, rank, world, local, args.exchange, args.c4_steps)
+    if not args.no_c5:
+        c5 = c5_leg(pkg, torch, dist if world > 1 else None, rank, world, local, args.exchange, args.c5_ticks)
     if rank == 0:
+        if parity is not None:
+            line["parity_check"] = parity
         if rbpf is not None:
             line["rbpf"] = rbpf
             if world == 1 and not args.no_cpu:
                 line["rbpf"]["cpu_baseline"] = rbpf_cpu("port")
+        if c4 is not None:
+            line["c4"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -501,6 +711,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-rbpf", action="store_true", help="skip the RBPF leg (BASELINE configs[2])")
     ap.add_argument("--rbpf-scans", type=int, default=20)
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_check leg (3 calls of a fresh handle against the CPU oracle)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 leg (BASELINE configs[3]: K=65536 T=128 obstacle term, strong scaling)")
+    ap.add_argument("--c4-steps", type=int, default=200)
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (BASELINE configs[4]: RBPF + MPPI closed loop at 50 Hz)")
+    ap.add_argument("--c5-ticks", type=int, default=300)
     ap.add_argument("--no-ramp", action="store_true", help="skip the untimed clock-ramp calls before the warm-up steps (ncu launch lists)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the [T][6] softmax partial travels - inside the update kernel over NVLink peer memory, or ncclAllGather")

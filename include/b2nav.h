@@ -192,7 +192,12 @@ void b2n_pf_destroy(b2n_pf *h);
  * Returns B2N_ERR_OFF_MAP where the reference would throw because an end point left the map. */
 int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3], const double cur_odom[3],
                 const double prev_odom[3], int icp_ok, const double icp_pose[3]);
-/* bmapping::ParticleFilter::getRobotState, particle_filter.cpp:255-274 -> (theta, x, y) */
+/* bmapping::ParticleFilter::getRobotState, particle_filter.cpp:255-274 -> (theta, x, y).
+ * On a SHARDED filter (b2n_pf_comm_init + b2n_pf_p2p_init) this, b2n_pf_new_map and b2n_pf_write_distance_field return the
+ * argmax over the particles of ALL ranks, read from the owning GPU over peer memory; they are then COLLECTIVE: every rank
+ * calls the same function between the same two SLAM() calls (two small all-reduces keep a rank from moving its particles
+ * while another still reads them).  Without peer memory they return B2N_ERR_UNSUPPORTED on a sharded filter.
+ * In the same way a sharded SLAM() fails on EVERY rank when any rank's particles or end points left the map. */
 int b2n_pf_get_robot_state(b2n_pf *h, double pose[3]);
 /* bmapping::ParticleFilter::newMap, particle_filter.cpp:277-291 + grid_mapper.cpp:185-226 */
 int b2n_pf_new_map(b2n_pf *h, int8_t *out, size_t count);

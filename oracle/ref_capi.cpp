@@ -174,6 +174,34 @@ void ref_feedforward(double base, double radius, const double pose[3], const dou
   out[0] = q.theta; out[1] = q.x; out[2] = q.y;
 }
 
+// a DiffDrive that lives across calls: the simulated robot / the odometer of the closed-loop tests
+// (rigid2d/src/fake_diff_encoders_node.cpp:100-135, bmapping/src/turtle_mapping_node.cpp:456-472)
+void *ref_dd_create(const double pose[3], double base, double radius)
+{
+  rigid2d::Pose p; p.theta = pose[0]; p.x = pose[1]; p.y = pose[2];
+  return new rigid2d::DiffDrive(p, base, radius);
+}
+void ref_dd_destroy(void *h) { delete static_cast<rigid2d::DiffDrive *>(h); }
+void ref_dd_feedforward(void *h, double w, double vx)
+{
+  rigid2d::Twist2D v; v.w = w; v.vx = vx; v.vy = 0.0;
+  static_cast<rigid2d::DiffDrive *>(h)->feedforward(v);
+}
+void ref_dd_update_odometry(void *h, double left, double right, double vel[2])
+{
+  rigid2d::WheelVelocities v = static_cast<rigid2d::DiffDrive *>(h)->updateOdometry(left, right);
+  vel[0] = v.ul; vel[1] = v.ur;
+}
+// out: pose (theta, x, y), encoders (left, right), wheel velocities (ul, ur)
+void ref_dd_state(void *h, double out[7])
+{
+  rigid2d::DiffDrive *d = static_cast<rigid2d::DiffDrive *>(h);
+  rigid2d::Pose p = d->pose();
+  rigid2d::WheelEncoders e = d->getEncoders();
+  rigid2d::WheelVelocities v = d->wheelVelocities();
+  out[0] = p.theta; out[1] = p.x; out[2] = p.y; out[3] = e.left; out[4] = e.right; out[5] = v.ul; out[6] = v.ur;
+}
+
 // ----------------------------------------------------------------------------- MPPI ---------
 void *ref_mppi_create(double wheel_radius, double wheel_base, const double Q[3], const double R[2],
                       const double P1[3], double lambda, double max_wheel_vel, double ul_var, double ur_var,

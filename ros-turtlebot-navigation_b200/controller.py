@@ -53,6 +53,10 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_create(C.byref(p), C.byref(self._h)))
         self.rollouts = int(rollouts)
         self.steps = self._lib.b2n_mppi_steps(self._h)
+        # out-parameters of newControls(), made once: the call sits in 50 Hz loops and in the bench's end-to-end leg
+        self._ul, self._ur = C.c_double(), C.c_double()
+        self._pul, self._pur = C.byref(self._ul), C.byref(self._ur)
+        self._new_controls = self._lib.b2n_mppi_new_controls
 
     # ---- the reference's public methods ---------------------------------------------------
     def setInitialControls(self, uL, uR):
@@ -62,9 +66,10 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_set_waypoint(self._h, wpt.x, wpt.y, wpt.theta))
 
     def newControls(self, ps):
-        ul, ur = C.c_double(), C.c_double()
-        _capi.check(self._lib.b2n_mppi_new_controls(self._h, ps.x, ps.y, ps.theta, C.byref(ul), C.byref(ur)))
-        return WheelVelocities(ul.value, ur.value)
+        rc = self._new_controls(self._h, ps.x, ps.y, ps.theta, self._pul, self._pur)
+        if rc:
+            _capi.check(rc)
+        return WheelVelocities(self._ul.value, self._ur.value)
 
     # ---- noise seam, taps, bench hooks --------------------------------------------------------
     def seed(self, seed, first_call=0):

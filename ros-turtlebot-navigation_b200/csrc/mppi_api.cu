@@ -208,7 +208,7 @@ MppiArgs make_args(b2n_mppi *h, double x, double y, double theta)
   a.capture = h->capture;
   a.tma_store = h->tma_store ? 1 : 0;
   a.obs_on = h->obs_on; a.obs_xsize = h->obs_xsize; a.obs_ysize = h->obs_ysize;
-  a.obs_xmin = h->obs_xmin; a.obs_ymin = h->obs_ymin; a.obs_res = h->obs_res;
+  a.obs_xmin = h->obs_xmin; a.obs_ymin = h->obs_ymin; a.obs_res = h->obs_res; a.obs_inv_res = 1.0 / h->obs_res;
   a.obs_xmax = h->obs_xmin + h->obs_xsize * h->obs_res;
   a.obs_ymax = h->obs_ymin + h->obs_ysize * h->obs_res;
   a.obs_weight = h->obs_weight; a.obs_d0 = h->obs_d0; a.obs_off = h->obs_off; a.obs_dist = h->d_obs;

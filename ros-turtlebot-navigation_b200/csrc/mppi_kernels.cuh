@@ -61,7 +61,7 @@ struct MppiArgs
   int external_noise, capture, tma_store;
   // optional obstacle term (extension, see b2nav.h)
   int obs_on, obs_xsize, obs_ysize;
-  double obs_xmin, obs_ymin, obs_xmax, obs_ymax, obs_res, obs_weight, obs_d0, obs_off;
+  double obs_xmin, obs_ymin, obs_xmax, obs_ymax, obs_res, obs_inv_res, obs_weight, obs_d0, obs_off;
   const float *obs_dist;
   int obs_ti0, obs_tj0;       // first cell of the tile staged in shared memory (kMppiObsTile square), -1: no tile
   // buffers
@@ -117,11 +117,19 @@ constexpr int kMppiObsTile = 32;             // cells per side of the obstacle-f
 __device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, const float *tile, double x, double y)
 {
   if (!(x >= a.obs_xmin && x <= a.obs_xmax) || !(y >= a.obs_ymin && y <= a.obs_ymax)) return a.obs_off;
-  double i = floor((x - a.obs_xmin) / a.obs_res);
-  if (i == (double)a.obs_xsize) i -= 1.0;
-  double j = floor((y - a.obs_ymin) / a.obs_res);
-  if (j == (double)a.obs_ysize) j -= 1.0;
-  const int ii = (int)i, jj = (int)j;
+  // floor((x - xmin) / res) as the oracle computes it, on the fp64 add / multiply pipe only (the division and the
+  // double -> integer conversions run at a fraction of its rate): the product with 1 / res is within a few ulps of the
+  // quotient, so unless it lands within 1e-9 of an integer both floors agree; the floor itself comes from the
+  // round-to-nearest of adding 1.5 * 2^52 (the integer is then the sum's low word), one less when that rounded up
+  const double kMagic = 6755399441055744.0;
+  const double qx = (x - a.obs_xmin) * a.obs_inv_res, qy = (y - a.obs_ymin) * a.obs_inv_res;
+  const double tx = qx + kMagic, ty = qy + kMagic;
+  const double rx = tx - kMagic, ry = ty - kMagic;          // rint(qx), rint(qy)
+  int ii = __double2loint(tx) - (rx > qx ? 1 : 0), jj = __double2loint(ty) - (ry > qy ? 1 : 0);
+  if (fabs(qx - rx) < 1e-9 * (qx + 1.0)) ii = (int)floor((x - a.obs_xmin) / a.obs_res);
+  if (fabs(qy - ry) < 1e-9 * (qy + 1.0)) jj = (int)floor((y - a.obs_ymin) / a.obs_res);
+  if (ii == a.obs_xsize) ii -= 1;
+  if (jj == a.obs_ysize) jj -= 1;
   const unsigned ti = (unsigned)(ii - a.obs_ti0), tj = (unsigned)(jj - a.obs_tj0);
   float df;
   if (a.obs_ti0 >= 0 && ti < (unsigned)kMppiObsTile && tj < (unsigned)kMppiObsTile) df = tile[ti * kMppiObsTile + tj];

@@ -30,7 +30,10 @@ struct b2n_pf
   cudaStream_t own_stream = nullptr, stream = nullptr;
   float *d_scan = nullptr, *h_scan = nullptr;
   double *d_beam_cs = nullptr, *d_pz = nullptr;
-  int *d_status = nullptr;            // [0] status bits, [1] N_eff, [2] resampled, [3] best index
+  int *d_status = nullptr;            // [0] status bits, [1] N_eff, [2] resampled, [3] best particle's index in its owner's set, [4] owner rank;
+                                      // [8 ..] every rank's status bits (sharded: gathered next to the weights)
+  PfPlanes *d_own_sets = nullptr;     // device copy of set[0], set[1]
+  bool global_w_valid = false;        // d_w / d_anc describe the particle set (set by SLAM, cleared by the weight tap)
   int *h_status = nullptr;            // pinned mirror
   double *d_w = nullptr;              // [n_total]
   int32_t *d_anc = nullptr;           // [n_total]
@@ -500,9 +503,11 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
 
   B2N_TRY(cudaMalloc(&h->d_scan, sizeof(float) * h->max_beams));
   B2N_TRY(cudaMallocHost(&h->h_scan, sizeof(float) * h->max_beams));
-  B2N_TRY(cudaMalloc(&h->d_status, 4 * sizeof(int)));
-  B2N_TRY(cudaMemsetAsync(h->d_status, 0, 4 * sizeof(int), h->stream));
-  B2N_TRY(cudaMallocHost(&h->h_status, 4 * sizeof(int)));
+  B2N_TRY(cudaMalloc(&h->d_status, (8 + kPfMaxRanks) * sizeof(int)));
+  B2N_TRY(cudaMemsetAsync(h->d_status, 0, (8 + kPfMaxRanks) * sizeof(int), h->stream));
+  B2N_TRY(cudaMalloc(&h->d_own_sets, 2 * sizeof(PfPlanes)));
+  B2N_TRY(cudaMemcpyAsync(h->d_own_sets, h->set, 2 * sizeof(PfPlanes), cudaMemcpyHostToDevice, h->stream));
+  B2N_TRY(cudaMallocHost(&h->h_status, (8 + kPfMaxRanks) * sizeof(int)));
   B2N_TRY(cudaMalloc(&h->d_w, sizeof(double) * h->n_total));
   B2N_TRY(cudaMalloc(&h->d_anc, sizeof(int32_t) * h->n_total));
   h->h_anc.assign(h->n_total, 0);
@@ -554,7 +559,7 @@ void b2n_pf_destroy(b2n_pf *h)
   cudaFree(h->d_peer_sets);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   free_planes(h->set[0]); free_planes(h->set[1]);
-  cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_w); cudaFree(h->d_anc);
+  cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_own_sets); cudaFree(h->d_w); cudaFree(h->d_anc);
   cudaFree(h->d_ext); cudaFree(h->d_samples); cudaFree(h->d_spill); cudaFree(h->d_stats); cudaFree(h->d_best); cudaFree(h->d_map);
   cudaFree(h->d_lik); cudaFree(h->d_idx);
   if (h->h_scan) cudaFreeHost(h->h_scan);
@@ -644,7 +649,12 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   h->launches++;
   if (h->nranks > 1) {
     // weights of all ranks in global particle order: one allgather; every rank then runs the identical walk
-    ncclResult_t r = ncclAllGather(w_local, h->d_w, (size_t)h->N, ncclDouble, h->comm, h->stream);
+    // ... and, in the same group, every rank's status bits: a rank that left the map (or ran out of heap) makes EVERY rank
+    // return the error below, so that none of them enters the migration alone and `cur` / `call` stay in step
+    ncclResult_t r = ncclGroupStart();
+    if (r == ncclSuccess) r = ncclAllGather(w_local, h->d_w, (size_t)h->N, ncclDouble, h->comm, h->stream);
+    if (r == ncclSuccess) r = ncclAllGather(h->d_status, h->d_status + 8, 1, ncclInt32, h->comm, h->stream);
+    if (r == ncclSuccess) r = ncclGroupEnd();
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
   }
   PfResample rs;
@@ -652,16 +662,18 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
   PfCall qn = q;
   qn.ext = h->ext_armed ? h->d_ext + (size_t)h->N * per : nullptr;
   qn.ext_per = 0;
-  rbpf_normalize_kernel<<<1, 32, 0, h->stream>>>(rs, h->n_total, qn);
+  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total, qn);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
   rbpf_scatter_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, w_local, h->N);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
-  B2N_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B2N_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, (8 + (h->nranks > 1 ? h->nranks : 0)) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   h->ext_armed = false;
-  const int status = h->h_status[0];
+  int status = h->h_status[0];
+  for (int r = 0; r < (h->nranks > 1 ? h->nranks : 0); r++) status |= h->h_status[8 + r];
+  h->global_w_valid = false;
   if (status & kPfStatusOffMap) {
     set_error("a beam end point or a particle pose left the map (reference: world2Grid / world2RowMajor throw, grid_mapper.cpp:817-825,854-862)");
     return B2N_ERR_OFF_MAP;
@@ -700,6 +712,7 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
     cudaEventElapsedTime(&h->last_ms[2], h->ev[4], h->ev[5]);
   }
   h->call++;
+  h->global_w_valid = true;
   return B2N_OK;
 }
 
@@ -725,8 +738,36 @@ int b2n_pf_likelihoods(b2n_pf *h, const float *scan, int n_beams, double *out, s
   return B2N_OK;
 }
 
+// sharded filter: every rank has reached this point of its stream (one small all-reduce)
+static int pf_barrier(b2n_pf *h)
+{
+  if (h->nranks <= 1) return B2N_OK;
+  ncclResult_t r = ncclAllReduce(h->d_status + 5, h->d_status + 6, 1, ncclInt32, ncclSum, h->comm, h->stream);
+  B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllReduce: %s", ncclGetErrorString(r));
+  return B2N_OK;
+}
+
+// the sets the best particle may live in: this rank's current set, or (sharded) every rank's current set
+static const PfPlanes *best_sets(const b2n_pf *h)
+{
+  return h->nranks > 1 ? h->d_peer_sets + (size_t)h->cur * h->nranks : h->d_own_sets + h->cur;
+}
+
+// argmax of the weights over the WHOLE filter (particle_filter.cpp:255-274): d_status[3..4] = (index, owner), d_best = pose, weight
 static int run_best(b2n_pf *h)
 {
+  if (h->nranks > 1) {
+    B2N_REQUIRE(h->p2p_ready, B2N_ERR_UNSUPPORTED,
+                "the best particle of a sharded filter may live on another GPU: b2n_pf_p2p_init (peer memory) is required");
+    B2N_REQUIRE(h->global_w_valid, B2N_ERR_UNSUPPORTED, "sharded filter: the weights changed since the last SLAM() (test tap)");
+    // every rank's SLAM() - its resampling copies included - is complete before anyone reads a peer's set
+    if (int rc = pf_barrier(h)) return rc;
+    rbpf_best_global_kernel<<<1, 1024, 0, h->stream>>>(h->d_w, h->d_anc, h->last_resampled, h->n_total, h->N, h->d_status + 3, h->d_best);
+    rbpf_fetch_pose_kernel<<<1, 1, 0, h->stream>>>(best_sets(h), h->d_status + 3, h->d_best);
+    B2N_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return B2N_OK;
+  }
   rbpf_best_kernel<<<1, 1024, 0, h->stream>>>(h->set[h->cur].meta, h->N, h->d_status + 3, h->d_best);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
@@ -738,6 +779,7 @@ int b2n_pf_get_robot_state(b2n_pf *h, double pose[3])
   B2N_REQUIRE(h && pose, B2N_ERR_INVALID_ARGUMENT, "null argument");
   if (int rc = set_device(h)) return rc;
   if (int rc = run_best(h)) return rc;
+  if (int rc = pf_barrier(h)) return rc;      // ... and every rank has read before anyone's next SLAM() moves the particles
   B2N_CUDA(cudaMemcpyAsync(h->h_best, h->d_best, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   pose[0] = h->h_best[0]; pose[1] = h->h_best[1]; pose[2] = h->h_best[2];
@@ -750,9 +792,10 @@ int b2n_pf_new_map(b2n_pf *h, int8_t *out, size_t count)
   B2N_REQUIRE(count == (size_t)h->c.G, B2N_ERR_INVALID_ARGUMENT, "map count %zu, expected %d cells", count, h->c.G);
   if (int rc = set_device(h)) return rc;
   if (int rc = run_best(h)) return rc;
-  rbpf_export_map_kernel<<<(h->c.G + 255) / 256, 256, 0, h->stream>>>(h->c, h->set[h->cur].log_odds, h->d_status + 3, h->d_map);
+  rbpf_export_map_kernel<<<(h->c.G + 255) / 256, 256, 0, h->stream>>>(h->c, best_sets(h), h->d_status + 3, h->d_map);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
+  if (int rc = pf_barrier(h)) return rc;
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   B2N_CUDA(cudaMemcpy(out, h->d_map, count, cudaMemcpyDeviceToHost));
   return B2N_OK;
@@ -786,6 +829,7 @@ int b2n_pf_set_weights(b2n_pf *h, const double *w, size_t count)
   if (int rc = read_meta(h, m)) return rc;
   for (int i = 0; i < h->N; i++) m[i].weight = w[i];
   B2N_CUDA(cudaMemcpy(h->set[h->cur].meta, m.data(), sizeof(PfParticle) * h->N, cudaMemcpyHostToDevice));
+  h->global_w_valid = false;
   return B2N_OK;
 }
 
@@ -844,7 +888,7 @@ int b2n_pf_normalize_resample(b2n_pf *h)
   rbpf_gather_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, h->d_w, h->N);
   PfResample rs;
   rs.w = h->d_w; rs.ancestors = h->d_anc; rs.info = h->d_status + 1;
-  rbpf_normalize_kernel<<<1, 32, 0, h->stream>>>(rs, h->n_total, q);
+  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total, q);
   rbpf_scatter_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, h->d_w, h->N);
   B2N_CUDA(cudaGetLastError());
   h->launches += 3;
@@ -927,7 +971,8 @@ int b2n_pf_write_distance_field(b2n_pf *h, float *device_out, size_t count)
   B2N_REQUIRE(h->nranks == 1, B2N_ERR_UNSUPPORTED, "single-rank operation (the best particle may live on another GPU)");
   if (int rc = set_device(h)) return rc;
   if (int rc = run_best(h)) return rc;
-  rbpf_export_distance_kernel<<<(h->c.G + 255) / 256, 256, 0, h->stream>>>(h->c, h->set[h->cur].d2, h->d_status + 3, h->max_occ_dist, device_out);
+  rbpf_export_distance_kernel<<<(h->c.G + 255) / 256, 256, 0, h->stream>>>(h->c, best_sets(h), h->d_status + 3, h->max_occ_dist, device_out);
+  if (int rc = pf_barrier(h)) return rc;
   B2N_CUDA(cudaGetLastError());
   h->launches++;
   B2N_CUDA(cudaStreamSynchronize(h->stream));

@@ -1086,68 +1086,115 @@ struct PfResample
   int *info;            // [0] = N_eff as printed, [1] = resampled
 };
 
-// one warp; every lane runs the same sequential fp64 chain on values fetched 32 at a time
-__global__ void __launch_bounds__(32) rbpf_normalize_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
+// normalizeWeights + effectiveParticles + lowVarianceResampling (particle_filter.cpp:442-500) on the gathered weights of
+// ALL ranks.  Bit-exact ancestors need the reference's sequential fp64 order: one sum, one sum of squares and one
+// cumulative walk, each a chain of dependent additions (about 8 cycles an element on this part) that no amount of
+// parallelism shortens - so the kernel makes sure the chains wait for nothing else.  One CTA: thread 0 runs the sum and
+// the sum-of-squares chains, thread 32 runs the walk, both out of shared memory; every other thread streams the weights in
+// (a chunk ahead, double buffered), divides them by the sum in parallel (the division is per element, not part of a chain)
+// and writes them back.  The walk starts together with the sum of squares, before N_eff is known, and its ancestors are
+// replaced by the identity when the filter does not resample.
+constexpr int kPfMaxRanks = 64;
+constexpr int kNormThreads = 256;
+constexpr int kNormChunk = 2048;       // weights per buffer
+
+__global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
 {
-  const int lane = threadIdx.x;
-  // sequential sums in index order (:442-465); the next 32 weights are already in flight while a chunk is consumed
+  __shared__ double buf[2][kNormChunk];
+  __shared__ double s_sum;
+  __shared__ int s_resample;
+  const int tid = threadIdx.x;
+  const int n_chunks = (n_total + kNormChunk - 1) / kNormChunk;
+  // chunk c into its buffer, by the `nload` threads that are not running a chain at the moment (lrank = 0 .. nload - 1)
+  auto load_chunk = [&](int c, bool normalise, double sum, int lrank, int nload) {
+    double *b = buf[c & 1];
+    for (int i = lrank; i < kNormChunk; i += nload) {
+      const int idx = c * kNormChunk + i;
+      double v = 0.0;
+      if (idx < n_total) {
+        v = r.w[idx];
+        if (normalise) { v = v / sum; r.w[idx] = v; }                      // :451
+      }
+      b[i] = v;
+    }
+  };
+  // ---- sum in index order (:446-449) --------------------------------------------------------------------------------------
+  load_chunk(0, false, 0.0, tid, kNormThreads);
+  __syncthreads();
   double sum = 0.0;
-  double nxt = lane < n_total ? r.w[lane] : 0.0;
-  for (int base = 0; base < n_total; base += 32) {
-    const double v = nxt;
-    nxt = base + 32 + lane < n_total ? r.w[base + 32 + lane] : 0.0;
-    const int cnt = min(32, n_total - base);
-    for (int i = 0; i < cnt; i++) sum += __shfl_sync(kFullMask, v, i);
+  for (int c = 0; c < n_chunks; c++) {
+    if (tid == 0) {
+      const double *b = buf[c & 1];
+      const int cnt = min(kNormChunk, n_total - c * kNormChunk);
+      int i = 0;
+      for (; i + 8 <= cnt; i += 8) {
+        const double v0 = b[i], v1 = b[i + 1], v2 = b[i + 2], v3 = b[i + 3], v4 = b[i + 4], v5 = b[i + 5], v6 = b[i + 6], v7 = b[i + 7];
+        sum += v0; sum += v1; sum += v2; sum += v3; sum += v4; sum += v5; sum += v6; sum += v7;
+      }
+      for (; i < cnt; i++) sum += b[i];
+    } else if (c + 1 < n_chunks) {
+      load_chunk(c + 1, false, 0.0, tid - 1, kNormThreads - 1);
+    }
+    __syncthreads();
   }
-  double sq = 0.0;
-  nxt = lane < n_total ? r.w[lane] : 0.0;
-  for (int base = 0; base < n_total; base += 32) {
-    double v = 0.0;
-    if (base + lane < n_total) { v = nxt / sum; r.w[base + lane] = v; }
-    nxt = base + 32 + lane < n_total ? r.w[base + 32 + lane] : 0.0;
-    const int cnt = min(32, n_total - base);
-    for (int i = 0; i < cnt; i++) { const double wi = __shfl_sync(kFullMask, v, i); sq += wi * wi; }   // std::pow(w, 2)
+  if (tid == 0) s_sum = sum;
+  __syncthreads();
+  sum = s_sum;
+  // ---- w /= sum, sum of squares (:451-457, 463) and, side by side, the low-variance walk (:468-500) -------------------------
+  // Equivalent to the reference's nested loops: sample m takes the first i with U_m <= w_0 + ... + w_i, clamped to
+  // N - 1 when the weights run out.
+  double z = 0.0;
+  if (tid == 32) {
+    if (q.ext) z = q.ext[(size_t)q.ext_per];                               // caller passes a pointer to the last variate
+    else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
   }
-  __syncwarp();
-  const int neff = (int)(1.0 / sq);                                        // :463-464
-  const bool resample = neff < (n_total / 2);
-  if (lane == 0) { r.info[0] = neff; r.info[1] = resample ? 1 : 0; }
-  if (!resample) {
-    for (int m = lane; m < n_total; m += 32) r.ancestors[m] = m;
-    return;
-  }
-  // the low-variance walk (:468-500), streamed: the weights come 32 at a time through one coalesced load and are handed
-  // out by shuffle, every lane runs the same sequential chain (cumulative sum and comparisons in the reference's
-  // order), lane 0 records the ancestors.  Equivalent to the reference's nested loops: sample m takes the first i with
-  // U_m <= w_0 + ... + w_i, clamped to N - 1 when the weights run out.
-  double z;
-  if (q.ext) z = q.ext[(size_t)q.ext_per];                                 // caller passes a pointer to the last variate
-  else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
   const double rr = z / (double)n_total;                                   // :475-476
   const double step = 1.0 / (n_total - 1);
-  double chunk = lane < n_total ? r.w[lane] : 0.0;
-  double ahead = 32 + lane < n_total ? r.w[32 + lane] : 0.0;
-  double cacc = __shfl_sync(kFullMask, chunk, 0);
-  int i = 0, m = 0;
+  double sq = 0.0, cacc = 0.0;
+  int m = 0;
   double U = rr + (double)(m * step);                                      // :485
-  for (;;) {
-    while (m < n_total && !(U > cacc)) {
-      if (lane == 0) r.ancestors[m] = i;
-      m++;
-      U = rr + (double)(m * step);
+  load_chunk(0, true, sum, tid, kNormThreads);
+  __syncthreads();
+  for (int c = 0; c < n_chunks; c++) {
+    const double *b = buf[c & 1];
+    const int cnt = min(kNormChunk, n_total - c * kNormChunk);
+    if (tid == 0) {
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        const double v0 = b[i], v1 = b[i + 1], v2 = b[i + 2], v3 = b[i + 3];
+        const double p0 = v0 * v0, p1 = v1 * v1, p2 = v2 * v2, p3 = v3 * v3;    // std::pow(w, 2)
+        sq += p0; sq += p1; sq += p2; sq += p3;
+      }
+      for (; i < cnt; i++) { const double v = b[i]; sq += v * v; }
+    } else if (tid == 32) {
+      for (int i = 0; i < cnt && m < n_total; i++) {
+        cacc += b[i];                                                      // c = w_0, then c += w_i (:481,492)
+        const int gi = c * kNormChunk + i;
+        if (gi == n_total - 1) {
+          // the weights are exhausted: every remaining sample clamps to N - 1 (:488-491)
+          while (m < n_total) { r.ancestors[m] = gi; m++; }
+          break;
+        }
+        while (m < n_total && !(U > cacc)) {
+          r.ancestors[m] = gi;
+          m++;
+          U = rr + (double)(m * step);
+        }
+      }
+    } else if (c + 1 < n_chunks) {
+      load_chunk(c + 1, true, sum, tid - (tid > 32 ? 2 : 1), kNormThreads - 2);
     }
-    if (m >= n_total) break;
-    i++;
-    if (i > n_total - 1) {                                                 // weights exhausted: the rest clamps to N - 1
-      for (int k = m + lane; k < n_total; k += 32) r.ancestors[k] = n_total - 1;
-      break;
-    }
-    if ((i & 31) == 0) {
-      chunk = ahead;
-      ahead = i + 32 + lane < n_total ? r.w[i + 32 + lane] : 0.0;
-    }
-    cacc += __shfl_sync(kFullMask, chunk, i & 31);
+    __syncthreads();
   }
+  if (tid == 0) {
+    const int neff = (int)(1.0 / sq);                                      // :463-464
+    const bool resample = neff < (n_total / 2);
+    r.info[0] = neff; r.info[1] = resample ? 1 : 0;
+    s_resample = resample ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_resample)
+    for (int k = tid; k < n_total; k += kNormThreads) r.ancestors[k] = k;
 }
 
 __global__ void rbpf_gather_weights_kernel(const PfParticle *meta, double *w, int n)
@@ -1250,29 +1297,73 @@ __global__ void __launch_bounds__(1024) rbpf_best_kernel(const PfParticle *meta,
     }
     if (threadIdx.x == 0) {
       const int b = (bi == 0x7FFFFFFF) ? 0 : bi;
-      *best = b;
+      best[0] = b; best[1] = 0;
       best_pose_weight[0] = meta[b].pose[0]; best_pose_weight[1] = meta[b].pose[1]; best_pose_weight[2] = meta[b].pose[2];
       best_pose_weight[3] = bw;
     }
   }
 }
 
+// the same argmax over a SHARDED filter: every rank holds the normalised weights of all ranks (the allgather of the last
+// SLAM call) and the ancestor list, so the weight of global slot m after that call is w[anc[m]] (w[m] when the filter did
+// not resample) - no communication.  best = (index in the owner's set, owner rank); the pose is then read from the owner's
+// memory (CUDA IPC mapping, the same one the resampling copies use).
+__global__ void __launch_bounds__(1024) rbpf_best_global_kernel(const double *w, const int32_t *anc, int resampled, int n_total, int n_local, int *best,
+                                                                double *best_weight)
+{
+  __shared__ double sw[32];
+  __shared__ int si[32];
+  double bw = 0.0;
+  int bi = 0x7FFFFFFF;
+  for (int i = threadIdx.x; i < n_total; i += blockDim.x) {
+    const double v = w[resampled ? anc[i] : i];
+    if (v > bw) { bw = v; bi = i; }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ow = __shfl_xor_sync(kFullMask, bw, d);
+    const int oi = __shfl_xor_sync(kFullMask, bi, d);
+    if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sw[threadIdx.x >> 5] = bw; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bw = threadIdx.x < (blockDim.x >> 5) ? sw[threadIdx.x] : 0.0;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7FFFFFFF;
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ow = __shfl_xor_sync(kFullMask, bw, d);
+      const int oi = __shfl_xor_sync(kFullMask, bi, d);
+      if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      const int b = (bi == 0x7FFFFFFF) ? 0 : bi;
+      best[0] = b % n_local; best[1] = b / n_local;
+      best_weight[3] = bw;
+    }
+  }
+}
+
+__global__ void rbpf_fetch_pose_kernel(const PfPlanes *sets, const int *which, double *best_pose_weight)
+{
+  const PfParticle *p = sets[which[1]].meta + which[0];
+  best_pose_weight[0] = p->pose[0]; best_pose_weight[1] = p->pose[1]; best_pose_weight[2] = p->pose[2];
+}
+
 // distance field of one particle as fp32 metres (Cell::occ_dist = sqrt(d2) * resolution, max_occ_dist where never reached)
-__global__ void rbpf_export_distance_kernel(const __grid_constant__ PfConst c, const uint32_t *d2, const int *which, double max_occ_dist,
+__global__ void rbpf_export_distance_kernel(const __grid_constant__ PfConst c, const PfPlanes *sets, const int *which, double max_occ_dist,
                                             float *out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.G) return;
-  const uint32_t v = d2[(size_t)(*which) * c.gstride + i];
+  const uint32_t v = sets[which[1]].d2[(size_t)which[0] * c.gstride + i];       // which = (index in its owner's set, owner rank)
   out[i] = (float)(v == kD2Unreached ? max_occ_dist : sqrt((double)v) * c.res);
 }
 
 // occupancy export of one particle: prob from the log-odds exactly as updateCellState left it, transposed output
-__global__ void rbpf_export_map_kernel(const __grid_constant__ PfConst c, const double *log_odds, const int *which, int8_t *out)
+__global__ void rbpf_export_map_kernel(const __grid_constant__ PfConst c, const PfPlanes *sets, const int *which, int8_t *out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.G) return;
-  const double l = log_odds[(size_t)(*which) * c.gstride + i];
+  const double l = sets[which[1]].log_odds[(size_t)which[0] * c.gstride + i];   // which = (index in its owner's set, owner rank)
   const int row = i / c.xsize, col = i - row * c.xsize;
   const int idx = col * c.xsize + row;                                      // grid_mapper.cpp:195-197
   int8_t v;

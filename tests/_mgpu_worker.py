@@ -90,7 +90,8 @@ def main():
         f.seed(3)
         of = orc.OraclePf(num_particles=N, **q)
         of.noise_philox(3)
-        res = {"weights": 0.0, "poses": 0.0, "ancestors_equal": True, "resampled": 0, "map_equal": True, "migrated": 0}
+        res = {"weights": 0.0, "poses": 0.0, "ancestors_equal": True, "resampled": 0, "map_equal": True, "migrated": 0,
+               "best_pose": 0.0, "best_map_equal": True, "best_unsupported_without_peer_memory": False}
         for i in range(scans):
             scan = orc.room_scan(poses[i + 1], rng=rng)
             f.SLAM(scan, pkg.Twist2D(*twists[i]), pkg.Pose(*poses[i + 1]), pkg.Pose(*poses[i]))
@@ -110,6 +111,15 @@ def main():
                 res["map_equal"] &= bool(np.array_equal(gg["log_odds"], go["log_odds"]) and np.array_equal(gg["occ_dist"], go["occ_dist"]))
                 res["map_equal"] &= bool(np.array_equal(f.occOrder(j), of.occ_order(rank * Nl + j)))
             res["migrated"] += f.migration()[0]
+            # the filter's answer = the best particle of ALL ranks (particle_filter.cpp:255-291), wherever it lives
+            if mode == "p2p":
+                res["best_pose"] = max(res["best_pose"], float(np.max(np.abs(np.subtract(f.getRobotState().displacement(), of.robot_state())))))
+                res["best_map_equal"] &= bool(np.array_equal(f.newMap(), of.new_map()))
+            elif i == 0:
+                try:
+                    f.getRobotState()
+                except pkg.B2NError as e:
+                    res["best_unsupported_without_peer_memory"] = e.code == -4
         out["rbpf_" + mode] = res
         dist.barrier()
         f.close()

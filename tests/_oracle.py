@@ -87,6 +87,12 @@ def ref_lib():
         L.ref_twist_to_wheels.argtypes = [D, D, D, D, nd(np.float64)]
         L.ref_integrate_twist.argtypes = [nd(np.float64)] * 3
         L.ref_feedforward.argtypes = [D, D, nd(np.float64), nd(np.float64), nd(np.float64)]
+        L.ref_dd_create.restype = C.c_void_p
+        L.ref_dd_create.argtypes = [nd(np.float64), D, D]
+        L.ref_dd_destroy.argtypes = [C.c_void_p]
+        L.ref_dd_feedforward.argtypes = [C.c_void_p, D, D]
+        L.ref_dd_update_odometry.argtypes = [C.c_void_p, D, D, nd(np.float64)]
+        L.ref_dd_state.argtypes = [C.c_void_p, nd(np.float64)]
         L.ref_mppi_create.restype = C.c_void_p
         L.ref_mppi_create.argtypes = [D, D, C.POINTER(D), C.POINTER(D), C.POINTER(D), D, D, D, D, D, D, C.c_int]
         L.ref_mppi_destroy.argtypes = [C.c_void_p]
@@ -98,6 +104,49 @@ def ref_lib():
         L.ref_mppi_rollout.argtypes = [C.c_void_p, nd(np.float64), nd(np.float64), nd(np.float64), nd(np.float64)]
         _rlib = L
     return _rlib
+
+
+class RefDiffDrive:
+    """The compiled reference rigid2d::DiffDrive (oracle/_ref), kept alive across calls: the plant and the odometer of the
+    closed-loop tests.  Same method names and (theta, x, y) / tuple conventions as synthetic.DiffDrive."""
+
+    def __init__(self, pose=(0.0, 0.0, 0.0), wheel_base=0.16, wheel_radius=0.033):
+        self.L = ref_lib()
+        self.base, self.radius = float(wheel_base), float(wheel_radius)
+        self.h = self.L.ref_dd_create(np.asarray(pose, dtype=np.float64), self.base, self.radius)
+
+    def _state(self):
+        out = np.zeros(7)
+        self.L.ref_dd_state(self.h, out)
+        return out
+
+    def feedforward(self, w, vx, vy=0.0):
+        self.L.ref_dd_feedforward(self.h, float(w), float(vx))
+
+    def updateOdometry(self, left, right):
+        v = np.zeros(2)
+        self.L.ref_dd_update_odometry(self.h, float(left), float(right), v)
+        return float(v[0]), float(v[1])
+
+    def wheelsToTwist(self, ul, ur):
+        out = np.zeros(3)
+        self.L.ref_wheels_to_twist(self.base, self.radius, float(ul), float(ur), out)
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def pose(self):
+        return tuple(float(v) for v in self._state()[0:3])
+
+    def getEncoders(self):
+        return tuple(float(v) for v in self._state()[3:5])
+
+    def wheelVelocities(self):
+        return tuple(float(v) for v in self._state()[5:7])
+
+    def __del__(self):
+        try:
+            self.L.ref_dd_destroy(self.h)
+        except Exception:
+            pass
 
 
 def _vp(a):

@@ -1,6 +1,7 @@
 """BASELINE configs[4] in miniature: RBPF pose estimate -> MPPI wheel command -> plant -> odometry + lidar scan, tick by
 tick, the GPU stack and the CPU oracle stack fed the same scans and odometry (mppi_waypoints_node.cpp:231-282 and
-turtle_mapping_node.cpp:451-494 fused into one loop; the plant stands in for fake_diff_encoders + Gazebo).
+turtle_mapping_node.cpp:451-494 fused into one loop; the plant is the reference's rigid2d::DiffDrive, compiled in
+oracle/_ref, driven the way fake_diff_encoders drives it; the lidar is the analytic ray cast of the synthetic room).
 
 Every tick: the filter's best pose within 1e-9 of the oracle's, the controller's command within 1e-5, ancestors equal.
 """
@@ -13,9 +14,16 @@ pytestmark = pytest.mark.gpu
 
 
 def test_rbpf_feeds_mppi_closed_loop(gpu_pkg):
+    """The loop of the reference's nodes with the reference's OWN plant: the simulated robot is rigid2d::DiffDrive::feedforward
+    on the commanded twist scaled by 1 / frequency (fake_diff_encoders_node.cpp:100-135), its encoder angles feed two odometers
+    (DiffDrive::updateOdometry: the controller's pose source and the mapper's pf_drive, turtle_mapping_node.cpp:456-472), the
+    wheel command becomes a twist through DiffDrive::wheelsToTwist (mppi_waypoints_node.cpp:276), waypoints switch as in
+    mppi_waypoints_node.cpp:231-258 - all through the compiled reference (oracle/_ref)."""
     pkg = gpu_pkg
-    N, K, hor, dt, ticks = 48, 512, 0.5, 0.02, 8
+    syn = pkg.synthetic
+    N, K, hor, dt, ticks = 48, 512, 0.5, 0.02, 12
     scan_every = 2                                     # a lidar scan every other control tick
+    freq = 1.0 / dt
     rng = np.random.default_rng(21)
     start = (0.0, 0.6, 0.0)                            # theta, x, y
     q = dict(num_particles=N, init_pose=start, motion_noise=(2e-3, 1e-3, 1e-3))
@@ -29,30 +37,45 @@ def test_rbpf_feeds_mppi_closed_loop(gpu_pkg):
     om = orc.OracleMppi(hor, dt, K)
     m.seed(6)
     om.noise_philox(6)
-    m.setWaypoint(pkg.Pose(theta=0.0, x=1.6, y=0.3))
-    om.setWaypoint(1.6, 0.3, 0.0)
+    # waypoints: a short leg first so that the switch fires inside the test
+    sw = syn.WaypointSwitch([0.62, 1.6, 1.6], [0.0, 0.3, 1.0], [0.0, 0.0, 1.5707], 0.03)
+    wx, wy, wth = sw.current()
+    m.setWaypoint(pkg.Pose(theta=wth, x=wx, y=wy))
+    om.setWaypoint(wx, wy, wth)
 
-    true = (start[1], start[2], start[0])              # plant state x, y, theta
-    odom_prev = start
+    Plant = orc.RefDiffDrive if orc.have_ref() else syn.DiffDrive
+    robot = Plant(start, prm["wheel_base"], prm["wheel_radius"])       # the simulated robot (fake_diff_encoders)
+    odo = Plant(start, prm["wheel_base"], prm["wheel_radius"])         # the controller's odometer
+    pf_drive = Plant(start, prm["wheel_base"], prm["wheel_radius"])    # the mapper's odometer
+    prev_odom = start
     est = start
-    resampled = 0
+    resampled = switched = 0
     for k in range(ticks):
-        # controller on the current estimate
+        # waypoint bookkeeping, then the controller on the current pose estimate (mppi_waypoints_node.cpp:231-265)
+        nw = sw.update(est[1], est[2])
+        if nw is not None:
+            switched += 1
+            m.setWaypoint(pkg.Pose(theta=nw[2], x=nw[0], y=nw[1]))
+            om.setWaypoint(nw[0], nw[1], nw[2])
         v = m.newControls(pkg.Pose(theta=est[0], x=est[1], y=est[2]))
         c = om.newControls(est[1], est[2], est[0])
         assert max(abs(v.ul - c[0]), abs(v.ur - c[1])) / max(1e-3, abs(c[0]), abs(c[1])) < 1e-5, (k, v, c)
-        # plant + perfect wheel odometry
-        true = orc.unicycle_step(true, c[0], c[1], dt)
+        # the wheel command as a body twist (:276), the simulated robot one period further, the odometers on its encoders
+        w, vx, _ = robot.wheelsToTwist(c[0], c[1])
+        robot.feedforward(w / freq, vx / freq)
+        left, right = robot.getEncoders()
+        odo.updateOdometry(left, right)
+        est = odo.pose()
         if (k + 1) % scan_every:
             continue
-        odom_cur = (true[2], true[0], true[1])
-        dth = odom_cur[0] - odom_prev[0]
-        dist = np.hypot(odom_cur[1] - odom_prev[1], odom_cur[2] - odom_prev[2])
-        twist = (dth, dist, 0.0)                        # body twist integrated over the scan interval
-        scan = orc.room_scan(odom_cur, rng=rng)
-        f.SLAM(scan, pkg.Twist2D(*twist), pkg.Pose(*odom_cur), pkg.Pose(*odom_prev))
-        of.slam(scan, twist, odom_cur, odom_prev)
-        odom_prev = odom_cur
+        # the mapper: odometry since the last scan, the twist of the wheel velocities, SLAM (turtle_mapping_node.cpp:466-494)
+        pf_drive.updateOdometry(left, right)
+        cur_odom = pf_drive.pose()
+        twist = pf_drive.wheelsToTwist(*pf_drive.wheelVelocities())
+        scan = orc.room_scan(robot.pose(), rng=rng)
+        f.SLAM(scan, pkg.Twist2D(*twist), pkg.Pose(*cur_odom), pkg.Pose(*prev_odom))
+        of.slam(scan, twist, cur_odom, prev_odom)
+        prev_odom = cur_odom
         T = f.getRobotState().displacement()
         want = of.robot_state()
         assert np.max(np.abs(np.array(T) - want)) < 1e-9, (k, T, want)
@@ -61,8 +84,8 @@ def test_rbpf_feeds_mppi_closed_loop(gpu_pkg):
         assert (neff, rs) == (oneff, ors) and np.array_equal(anc, oanc)
         resampled += rs
         assert np.array_equal(f.newMap(), of.new_map())
-        est = tuple(want)
-    assert resampled >= 1
+        est = tuple(want)                               # the filter's pose replaces the odometer's until the next tick
+    assert resampled >= 1 and switched >= 1
 
 
 def test_filter_map_feeds_the_obstacle_term_on_the_device(gpu_pkg):

@@ -97,3 +97,43 @@ def test_beam_table_and_likelihood_table_match_the_oracle(pkg):
         assert rc == 0 and lik == pz[d2], (d, d2)
     assert len(pz) == 200 * 200 + 2
     assert pz[-1] == 0.95 * (1.0 / np.sqrt(2.0 * np.pi * 0.25)) * np.exp(-0.5 * (10.0 * 10.0) / 0.25) + 0.01 / 0.04
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs oracle/_ref (the compiled reference)")
+def test_synthetic_plant_is_the_reference_diff_drive(pkg):
+    """synthetic.DiffDrive / WaypointSwitch (the plant and node bookkeeping bench.py's closed-loop leg runs on) against the
+    compiled reference rigid2d::DiffDrive: a simulated robot driven by feedforward (fake_diff_encoders_node.cpp:100-135) and an
+    odometer fed its encoder angles (updateOdometry), 400 random commands incl. pure rotations, straight lines and stand-still:
+    poses, encoders and wheel velocities agree to the last bit or two (Python floats are C doubles on the same libm)."""
+    syn = pkg.synthetic
+    rng = np.random.default_rng(3)
+    start = (0.3, -0.2, 0.7)
+    robots = (syn.DiffDrive(start, 0.16, 0.033), orc.RefDiffDrive(start, 0.16, 0.033))
+    odos = (syn.DiffDrive(start, 0.16, 0.033), orc.RefDiffDrive(start, 0.16, 0.033))
+    for k in range(400):
+        kind = k % 8
+        ul, ur = rng.uniform(-6.3, 6.3, 2)
+        if kind == 5:
+            ul = ur
+        if kind == 6:
+            ul = -ur
+        if kind == 7:
+            ul = ur = 0.0
+        states = []
+        for rb, od in zip(robots, odos):
+            w, vx, vy = rb.wheelsToTwist(ul, ur)
+            rb.feedforward(w / 50.0, vx / 50.0)
+            el, er = rb.getEncoders()
+            vel = od.updateOdometry(el, er)
+            states.append(np.array(rb.pose() + rb.getEncoders() + rb.wheelVelocities() + od.pose() + tuple(vel) + od.wheelsToTwist(*vel)))
+        assert np.max(np.abs(states[0] - states[1])) < 1e-13, (k, states)
+    for a in np.concatenate([rng.uniform(-20, 20, 200), [0.0, np.pi, -np.pi, 3 * np.pi]]):
+        assert syn.normalize_angle_PI(float(a)) == orc.ref_lib().ref_normalize_angle_pi(float(a))
+    # the node's waypoint bookkeeping (mppi_waypoints_node.cpp:231-258) on the shipped pentagon
+    sw = syn.WaypointSwitch([0, 1, 1, 0.5, 0], [0, 0, 1, 2, 1], [0, 1.5707, 2.3562, -2.3562, -1.5707], 0.1)
+    assert sw.update(0.5, 0.5) is None and sw.wpt_id == 0
+    seen = []
+    for _ in range(6):
+        x, y, _th = sw.current()
+        seen.append(sw.update(x + 0.05, y))
+    assert [s[:2] for s in seen] == [(1, 0), (1, 1), (0.5, 2), (0, 1), (0, 0), (1, 0)] and sw.cycle_complete and sw.cnt == 6

@@ -27,5 +27,8 @@ def test_two_gpus_match_the_unsharded_oracle(gpu_pkg):
             assert rb["ancestors_equal"] and rb["map_equal"], mode      # resampling indices and maps bit-exact
             assert rb["weights"] < 1e-9 and rb["poses"] < 1e-9, mode
             assert rb["resampled"] >= 1
+        rb = res["rbpf_p2p"]
+        assert rb["best_pose"] < 1e-9 and rb["best_map_equal"]            # global argmax, read from the owning GPU
+        assert res["rbpf_nccl"]["best_unsupported_without_peer_memory"]
     for mode in ("rbpf_nccl", "rbpf_p2p"):
         assert sum(res[mode]["migrated"] for res in json.loads(line[len("MGPU_RESULT "):])) >= 1   # particles really changed GPU
