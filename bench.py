@@ -6,15 +6,18 @@
 One "step" is one controller::MPPI::newControls(): K rollouts x T time steps (noise, RK4 diff-drive
 integration, loss, cost-to-go, T softmaxes over K, control update).  At N GPUs every rank simulates
 its own K rollouts of an N*K-rollout job (weak scaling) and the per-step partial sums are exchanged
-with one ncclAllGather.  Rank 0 prints ONE JSON line.
+over NVLink peer memory inside the call's kernel (--exchange nccl: one ncclAllGather).  Rank 0 prints ONE JSON line.
+Extra keys: parity_check (a fresh handle against the CPU oracle), rbpf (configs[2]), c4 (configs[3], strong scaling),
+c5 (configs[4], closed loop).
 
   value     whole-job trajectory-steps/s with everything resident on the device: `steps` calls are
             queued back to back on one stream and timed with CUDA events (max over ranks).
   e2e       the same metric through the public synchronous call (host pose in, host controls out,
             one stream synchronisation per step).
-  roofline  the rollout kernel alone: algorithmic bytes (12 B per trajectory-step, the fp32 state
-            tensor) over its mean duration, `steps` launches back to back between two CUDA events
-            on the launching stream in a second pass; peak from MEASURED_PEAKS.json.
+  roofline  the rollout phase of the call's kernel alone (launched without its merger CTAs): algorithmic
+            bytes (12 B per trajectory-step, the fp32 state tensor) over its mean duration, `steps`
+            launches back to back between two CUDA events on the launching stream in a second pass;
+            peak from MEASURED_PEAKS.json.
   cpu_baseline  the CPU oracle port (oracle/liboracle_nav.so), one thread, on a bounded sample.
   --impl reference  times the UNMODIFIED reference controller::MPPI compiled at oracle/_ref
             (single thread: its RNG is one process-global engine) on bounded samples of the same
@@ -185,6 +188,7 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
     f.setKernelTiming(True)
     ms = [0.0, 0.0, 0.0]
     resampled, wall, migrated = 0, 0.0, 0
+    dup = []
     n0 = f.launchCount()
     for i in range(n_scans + warmup):
         if i == warmup:
@@ -199,7 +203,11 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
             k = f.kernelTimes()
             for j in range(3):
                 ms[j] += k[j]
-            resampled += f.resampleInfo()[1]
+            info = f.resampleInfo()
+            resampled += info[1]
+            if info[1]:
+                import numpy as np
+                dup.append(1.0 - len(np.unique(info[2])) / float(len(info[2])))
             migrated += f.migration()[0]
     launches = f.launchCount() - n0
     if world > 1:
@@ -225,6 +233,7 @@ def rbpf_gpu_leg(pkg, torch, n_scans, warmup, rank=0, world=1, local=0, dist=Non
         "config": {"workload": "RBPF 4096 particles per GPU, 360-beam synthetic lidar, 200x200 occupancy grid (BASELINE configs[2]), motion-model branch",
                    "particles_per_gpu": RBPF_N, "particles_total": n_all, "beams": RBPF_BEAMS, "cells": RBPF_CELLS, "scans": n_scans,
                    "warmup_scans": warmup, "resampled_scans": int(resampled), "particles_migrated_between_gpus": int(migrated),
+                   "duplicate_ancestor_fraction_per_resampling_scan": (sum(dup) / len(dup)) if dup else None,
                    "sharding": ("particles; weights allgather + identical walk + migration by %s" % ("peer-memory copy kernel over NVLink" if exchange == "p2p" else "ncclSend/ncclRecv")) if world > 1 else "none",
                    "l2": "per-particle planes total %.1f GB per GPU >> 126 MB L2" % (RBPF_N * RBPF_CELLS * 12 / 1e9)},
         "ms_per_scan": dev_ms / n_scans,
@@ -663,13 +672,14 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, requested_exchange), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24,
                     "d2h_bytes_per_step": 16,
-                    "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the update kernel into mapped pinned memory"},
+                    "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the call's kernel into mapped pinned memory (four 8-byte words, each tagged with the call's sequence number)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "mppi_rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "mppi_rollout_kernel (rollout phase: loop + CTA partials, launched without the merger CTAs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": k_ms, "kernel_samples": k_n,
                          "algorithmic_bytes_per_launch": K_ROLLOUTS * T * ALGO_BYTES_PER_TRAJ_STEP,
-                         "note": "fp64 parity kernel is FP64-pipe bound, not HBM bound (DESIGN.md)"},
+                         "traffic_source": "profiles/roofline_traffic.json: ncu range replay over 16 consecutive launches (tools/measure_traffic.sh)",
+                         "note": "the fp64 parity kernel is bound by instruction issue and dependent-instruction latency (ncu: 41 % issue-active at 20 warps per SM, FP64 pipe 25 %), not by HBM (DESIGN.md 3.3)"},
             "last_controls": [v.ul, v.ur],
         }
         if world == 1 and not args.no_cpu:

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <random>
 #include <vector>
 
 #if __has_include(<rigid2d/diff_drive.hpp>)
@@ -86,6 +87,10 @@ public:
     p.init_pose[0] = d.theta; p.init_pose[1] = d.x; p.init_pose[2] = d.y;   // particle_filter.cpp:133
     p.particle_offset = 0; p.particles_total = num_particles; p.device = -1; p.max_beams = 0;
     detail::check(b2n_pf_create(&p, &h_));
+    // like the reference, whose engine is seeded from std::random_device (particle_filter.cpp:17-22); b2n_pf_seed(handle(), ...)
+    // makes a run reproducible
+    std::random_device rd;
+    detail::check(b2n_pf_seed(h_, ((uint64_t)rd() << 32) | (uint64_t)rd(), 0));
     int xs = 0, ys = 0;
     detail::check(b2n_pf_grid_size(h_, &xs, &ys));
     cells_ = (size_t)xs * (size_t)ys;

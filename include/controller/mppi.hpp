@@ -18,6 +18,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <random>
 #include <vector>
 
 #if __has_include(<rigid2d/diff_drive.hpp>)
@@ -79,6 +80,10 @@ public:
     p.horizon = horizon; p.dt = dt;
     p.rollouts = rollouts; p.rollout_offset = 0; p.rollouts_total = rollouts; p.device = -1;
     detail::check(b2n_mppi_create(&p, &h_));
+    // like the reference, whose engine is seeded from std::random_device (rigid2d/src/rigid2d/utilities.cpp:12-17): every
+    // controller draws its own perturbation streams.  b2n_mppi_seed(handle(), ...) makes a run reproducible.
+    std::random_device rd;
+    detail::check(b2n_mppi_seed(h_, ((uint64_t)rd() << 32) | (uint64_t)rd(), 0));
   }
   ~MPPI() { b2n_mppi_destroy(h_); }
   MPPI(const MPPI &) = delete;

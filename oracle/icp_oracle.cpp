@@ -16,6 +16,29 @@
 //   * the wrapper keeps the previous scan and answers the first call with success and an untouched transform
 //     (cloud_alignment.cpp:37-72).
 // The GPU kernel is checked against THIS file; neither is claimed to reproduce PCL bit for bit.
+//
+// Known deviations from pcl::IterativeClosestPoint 1.8 as the reference configures it (cloud_alignment.cpp:166-195), listed
+// so that whoever pins this against a PCL build knows where to look (the row stays "partial / parity unpinned" until then):
+//   1. arithmetic: PCL aligns in float (Eigen::Matrix4f guess from float cos / sin, :172-181; float SVD of the 3x3
+//      covariance in TransformationEstimationSVD via Eigen::umeyama); here the pair sums and the closed-form planar solution
+//      are double, the points float.  Expect agreement to ~1e-6 in the transform, not bit parity.
+//   2. transformation estimation: PCL solves the 3-D problem by SVD; here its restriction to rotations about z (all
+//      points have z = 0, so the SVD's answer is that rotation) in closed form: theta = atan2(Sxy - Syx, Sxx + Syy).
+//   3. correspondence estimation: PCL queries a FLANN kd-tree (exact nearest neighbour, ties by tree order); here an
+//      exhaustive search, ties by lowest target index.  The correspondence distance test is squared distance <= 0.25 m^2
+//      in both (CorrespondenceEstimation::determineCorrespondences compares squared distances).
+//   4. RANSAC outlier rejection threshold 0.05 (:190): the setter stores a member that IterativeClosestPoint::
+//      computeTransformation never reads unless a CorrespondenceRejectorSampleConsensus is added to the rejector list,
+//      which the reference does not do; it has no effect there and none here.
+//   5. convergence (DefaultConvergenceCriteria): PCL counts consecutive "similar" iterations (max_iterations_similar_
+//      transforms_ = 0 by default, so the first similar iteration stops) and tests, in this order, iteration count,
+//      the incremental transform (cos of its rotation angle >= rotation_threshold_ = 0.99999 AND squared translation <=
+//      translation_threshold_, which IterativeClosestPoint sets to the transformation epsilon itself, 1e-8), then the
+//      absolute and the relative MSE change (mse_threshold_absolute_ = the euclidean
+//      fitness epsilon, mse_threshold_relative_ = 1e-5).  Restated in that order; hasConverged() is true for all three
+//      reasons including "iterations exhausted", which is why the reference's failure branch (:200-204) is in practice
+//      only reached through fewer than 3 correspondences.
+//   6. the final transform is the product of the increments applied to the guess, accumulated in double here (float in PCL).
 #include <cmath>
 #include <cstdint>
 #include <cstring>

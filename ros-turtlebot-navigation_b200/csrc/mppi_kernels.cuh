@@ -112,30 +112,38 @@ struct MppiUpdateArgs
 
 constexpr int kMppiObsTile = 32;             // cells per side of the obstacle-field tile staged through TMA
 
+// cell index of a coordinate exactly as the oracle computes it, floor((x - xmin) / res): the rare path of
+// mppi_obstacle_cost, kept out of line (an fp64 division is some forty instructions)
+__device__ __noinline__ int mppi_obstacle_cell_exact(double x, double xmin, double res) { return (int)floor((x - xmin) / res); }
+
 // the obstacle term of one state (extension, b2nav.h): the distance comes from the tile in shared memory when the cell
 // is inside it (every state of a horizon lies within a few cells of the start pose), from global memory otherwise
 __device__ __forceinline__ double mppi_obstacle_cost(const MppiArgs &a, const float *tile, double x, double y)
 {
-  if (!(x >= a.obs_xmin && x <= a.obs_xmax) || !(y >= a.obs_ymin && y <= a.obs_ymax)) return a.obs_off;
-  // floor((x - xmin) / res) as the oracle computes it, on the fp64 add / multiply pipe only (the division and the
-  // double -> integer conversions run at a fraction of its rate): the product with 1 / res is within a few ulps of the
-  // quotient, so unless it lands within 1e-9 of an integer both floors agree; the floor itself comes from the
-  // round-to-nearest of adding 1.5 * 2^52 (the integer is then the sum's low word), one less when that rounded up
+  const bool inside = (x >= a.obs_xmin) & (x <= a.obs_xmax) & (y >= a.obs_ymin) & (y <= a.obs_ymax);
+  // floor((x - xmin) / res) on the fp64 add / multiply pipe only (the division and the double -> integer conversions run
+  // at a fraction of its rate): the product with 1 / res is within a few ulps of the quotient, so unless it lands within
+  // 1e-6 of an integer both floors agree; the floor itself comes from the round-to-nearest of adding 1.5 * 2^52 (the
+  // integer is then the sum's low word), one less when that rounded up
   const double kMagic = 6755399441055744.0;
   const double qx = (x - a.obs_xmin) * a.obs_inv_res, qy = (y - a.obs_ymin) * a.obs_inv_res;
   const double tx = qx + kMagic, ty = qy + kMagic;
   const double rx = tx - kMagic, ry = ty - kMagic;          // rint(qx), rint(qy)
   int ii = __double2loint(tx) - (rx > qx ? 1 : 0), jj = __double2loint(ty) - (ry > qy ? 1 : 0);
-  if (fabs(qx - rx) < 1e-9 * (qx + 1.0)) ii = (int)floor((x - a.obs_xmin) / a.obs_res);
-  if (fabs(qy - ry) < 1e-9 * (qy + 1.0)) jj = (int)floor((y - a.obs_ymin) / a.obs_res);
-  if (ii == a.obs_xsize) ii -= 1;
-  if (jj == a.obs_ysize) jj -= 1;
+  const bool near = (fabs(qx - rx) < 1e-6) | (fabs(qy - ry) < 1e-6);     // (a product of at most a few thousand cells is off by < 1e-12)
+  if (near && inside) {
+    ii = mppi_obstacle_cell_exact(x, a.obs_xmin, a.obs_res);
+    jj = mppi_obstacle_cell_exact(y, a.obs_ymin, a.obs_res);
+  }
+  ii = max(0, min(ii, a.obs_xsize - 1));                    // x == xmax lands in cell xsize: the reference steps back (grid_mapper.cpp:866-875)
+  jj = max(0, min(jj, a.obs_ysize - 1));                    // (and an outside state reads a valid address; its value is not used)
   const unsigned ti = (unsigned)(ii - a.obs_ti0), tj = (unsigned)(jj - a.obs_tj0);
   float df;
   if (a.obs_ti0 >= 0 && ti < (unsigned)kMppiObsTile && tj < (unsigned)kMppiObsTile) df = tile[ti * kMppiObsTile + tj];
   else df = __ldg(&a.obs_dist[(size_t)ii * a.obs_ysize + jj]);       // row-major [xsize][ysize]
   const double pen = a.obs_d0 - (double)df;
-  return pen > 0.0 ? a.obs_weight * pen * pen : 0.0;
+  const double cost = pen > 0.0 ? a.obs_weight * pen * pen : 0.0;
+  return inside ? cost : a.obs_off;
 }
 
 // exp(x) for x <= 0.  Below the cut the result cannot change a softmax sum that already holds the minimum's 1.0, so
@@ -397,14 +405,14 @@ __device__ __forceinline__ void mppi_merge_sets(int T, int TP2, int n, double in
 
 // the control update of mppi.cpp:112-137 for step t from the fully merged sums (one thread)
 template <class A>
-__device__ __forceinline__ void mppi_apply_update(const A &a, const double *u_cur, int t, double m, double S, double Aw, double Bw, double DL, double DR)
+__device__ __forceinline__ void mppi_apply_update(const A &a, double ul_cur, double ur_cur, int t, double m, double S, double Aw, double Bw, double DL, double DR)
 {
   const int T = a.T;
   // w_k = exp(-(J_k - min)/lambda) + 1e-8, normalised (mppi.cpp:117-118)
   const double sumw = S + a.k_total * 1e-8;
   const double inv = 1.0 / sumw;
-  double nl = u_cur[t] + (Aw + 1e-8 * DL) * inv;            // mppi.cpp:120-121
-  double nr = u_cur[T + t] + (Bw + 1e-8 * DR) * inv;
+  double nl = ul_cur + (Aw + 1e-8 * DL) * inv;              // mppi.cpp:120-121
+  double nr = ur_cur + (Bw + 1e-8 * DR) * inv;
   nl = fmin(fmax(nl, -a.umax), a.umax);                     // mppi.cpp:124-125
   nr = fmin(fmax(nr, -a.umax), a.umax);
   if (t == 0) {                                             // mppi.cpp:129-131
@@ -562,6 +570,20 @@ template <int NT, bool FASTEXP>
 __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
 {
   const int t = (int)blockIdx.x - a.n_roll;
+  // this step of the current plan: fetched now, used after the wait (the plan does not change during the call)
+  // (a merger can be resident before the previous call has finished: the plan's step count first, as the rollout CTAs do)
+  double ul_cur = 0.0, ur_cur = 0.0;
+  if (threadIdx.x == 0) {
+    if (a.plan_need) {
+      unsigned long long seen;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.plan_seq) : "memory");
+        if (++spins == (1u << 28)) __trap();
+      } while (seen < a.plan_need);
+    }
+    ul_cur = a.u_plan[t]; ur_cur = a.u_plan[a.T + t];
+  }
   // the next grid in the stream (the kernel that draws the next call's variates) may take the SMs the rollout CTAs leave
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // every rollout CTA of this call has published its partial (a monotonic count over the handle's fused calls)
@@ -585,7 +607,7 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
   }
   if (a.nranks > 1) mppi_exchange_step<NT, FASTEXP>(a, t, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
-  mppi_apply_update(a, a.u_plan, t, m, S, A, B, DL, DR);
+  mppi_apply_update(a, ul_cur, ur_cur, t, m, S, A, B, DL, DR);
   // this step of the plan is complete: the next call's CTAs wait for all T
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.plan_seq), "l"(1ull) : "memory");
   mppi_stamp(a, 6);
@@ -1077,7 +1099,7 @@ __global__ void __launch_bounds__(kMppiUpdateThreads) mppi_update_kernel(const M
     o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
     return;
   }
-  mppi_apply_update(a, a.u_cur, t, m, S, A, B, DL, DR);
+  mppi_apply_update(a, a.u_cur[t], a.u_cur[a.T + t], t, m, S, A, B, DL, DR);
 }
 
 // parity tap: the normalised weights the reference materialises at mppi.cpp:117-118

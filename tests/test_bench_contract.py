@@ -30,8 +30,12 @@ def test_reference_arm_contract():
 
 @pytest.mark.gpu
 def test_gpu_arm_contract(gpu_pkg):
-    d = _line(["--steps", "50", "--warmup", "3", "--rbpf-scans", "2"])
-    assert COMMON <= set(d) and {"roofline", "clocks", "rbpf"} <= set(d)
+    d = _line(["--steps", "50", "--warmup", "3", "--rbpf-scans", "2", "--c4-steps", "20", "--c5-ticks", "20"])
+    assert COMMON <= set(d) and {"roofline", "clocks", "rbpf", "parity_check", "c4", "c5"} <= set(d)
+    pc = d["parity_check"]
+    assert pc["kernel_variant"] == "fast" and max(pc["controls_rel_err"], pc["plan_rel_err"], pc["states_rel_err"]) < 1e-5
+    assert d["c4"]["rollouts_per_gpu"] == 65536 and d["c4"]["kernel_variant"] == "fast" and d["c4"]["us_per_call"] > 0
+    assert d["c5"]["particles_total"] == 4096 and d["c5"]["meets_50hz_budget"] is True
     assert d["dtype"] == "f64" and d["gpu_launches"] == 100 and d["n_gpus"] == 1
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12

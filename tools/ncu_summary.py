@@ -50,6 +50,8 @@ def main():
     rd = csv.DictReader(io.StringIO("\n".join(lines[start:])))
     ex, st = defaultdict(int), defaultdict(int)
     for r in rd:
+        if r["Source"] == "Source" or not (r.get("Address") or "").startswith("0x"):
+            break                                   # the report holds more launches: the first one is summarised
         ins = r["Source"].split()
         if not ins:
             continue
