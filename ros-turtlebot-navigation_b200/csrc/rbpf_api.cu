@@ -36,6 +36,7 @@ struct b2n_pf
   bool global_w_valid = false;        // d_w / d_anc describe the particle set (set by SLAM, cleared by the weight tap)
   int *h_status = nullptr;            // pinned mirror
   double *d_w = nullptr;              // [n_total]
+  double *d_cum = nullptr;            // [n_total] cumulative normalised weights (the walk's c)
   int32_t *d_anc = nullptr;           // [n_total]
   std::vector<int32_t> h_anc;
   double *d_ext = nullptr;
@@ -509,6 +510,7 @@ int b2n_pf_create(const b2n_pf_params *params, b2n_pf **out)
   B2N_TRY(cudaMemcpyAsync(h->d_own_sets, h->set, 2 * sizeof(PfPlanes), cudaMemcpyHostToDevice, h->stream));
   B2N_TRY(cudaMallocHost(&h->h_status, (8 + kPfMaxRanks) * sizeof(int)));
   B2N_TRY(cudaMalloc(&h->d_w, sizeof(double) * h->n_total));
+  B2N_TRY(cudaMalloc(&h->d_cum, sizeof(double) * h->n_total));
   B2N_TRY(cudaMalloc(&h->d_anc, sizeof(int32_t) * h->n_total));
   h->h_anc.assign(h->n_total, 0);
   for (int i = 0; i < h->n_total; i++) h->h_anc[i] = i;
@@ -559,7 +561,7 @@ void b2n_pf_destroy(b2n_pf *h)
   cudaFree(h->d_peer_sets);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   free_planes(h->set[0]); free_planes(h->set[1]);
-  cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_own_sets); cudaFree(h->d_w); cudaFree(h->d_anc);
+  cudaFree(h->d_scan); cudaFree(h->d_beam_cs); cudaFree(h->d_pz); cudaFree(h->d_status); cudaFree(h->d_own_sets); cudaFree(h->d_w); cudaFree(h->d_cum); cudaFree(h->d_anc);
   cudaFree(h->d_ext); cudaFree(h->d_samples); cudaFree(h->d_spill); cudaFree(h->d_stats); cudaFree(h->d_best); cudaFree(h->d_map);
   cudaFree(h->d_lik); cudaFree(h->d_idx);
   if (h->h_scan) cudaFreeHost(h->h_scan);
@@ -658,13 +660,14 @@ int b2n_pf_slam(b2n_pf *h, const float *scan, int n_beams, const double twist[3]
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
   }
   PfResample rs;
-  rs.w = h->d_w; rs.ancestors = h->d_anc; rs.info = h->d_status + 1;
+  rs.w = h->d_w; rs.cum = h->d_cum; rs.ancestors = h->d_anc; rs.info = h->d_status + 1;
   PfCall qn = q;
   qn.ext = h->ext_armed ? h->d_ext + (size_t)h->N * per : nullptr;
   qn.ext_per = 0;
-  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total, qn);
+  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total);
+  rbpf_ancestors_kernel<<<(h->n_total + 255) / 256, 256, 0, h->stream>>>(rs, h->n_total, qn);
   B2N_CUDA(cudaGetLastError());
-  h->launches++;
+  h->launches += 2;
   rbpf_scatter_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, w_local, h->N);
   B2N_CUDA(cudaGetLastError());
   h->launches++;
@@ -887,11 +890,12 @@ int b2n_pf_normalize_resample(b2n_pf *h)
   q.ext_per = 0;
   rbpf_gather_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, h->d_w, h->N);
   PfResample rs;
-  rs.w = h->d_w; rs.ancestors = h->d_anc; rs.info = h->d_status + 1;
-  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total, q);
+  rs.w = h->d_w; rs.cum = h->d_cum; rs.ancestors = h->d_anc; rs.info = h->d_status + 1;
+  rbpf_normalize_kernel<<<1, kNormThreads, 0, h->stream>>>(rs, h->n_total);
+  rbpf_ancestors_kernel<<<(h->n_total + 255) / 256, 256, 0, h->stream>>>(rs, h->n_total, q);
   rbpf_scatter_weights_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(pl.meta, h->d_w, h->N);
   B2N_CUDA(cudaGetLastError());
-  h->launches += 3;
+  h->launches += 4;
   B2N_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B2N_CUDA(cudaMemcpyAsync(h->h_anc.data(), h->d_anc, sizeof(int32_t) * h->n_total, cudaMemcpyDeviceToHost, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));

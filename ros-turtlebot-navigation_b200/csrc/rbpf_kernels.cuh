@@ -1082,27 +1082,31 @@ __global__ void __launch_bounds__(kDfMaxWarps * 32, 1) rbpf_distance_field_group
 struct PfResample
 {
   double *w;            // [n_total] gathered weights in global particle order, normalised in place
+  double *cum;          // [n_total] cumulative sums of the normalised weights, in index order
   int32_t *ancestors;   // [n_total]
   int *info;            // [0] = N_eff as printed, [1] = resampled
 };
 
 // normalizeWeights + effectiveParticles + lowVarianceResampling (particle_filter.cpp:442-500) on the gathered weights of
-// ALL ranks.  Bit-exact ancestors need the reference's sequential fp64 order: one sum, one sum of squares and one
-// cumulative walk, each a chain of dependent additions (about 8 cycles an element on this part) that no amount of
-// parallelism shortens - so the kernel makes sure the chains wait for nothing else.  One CTA: thread 0 runs the sum and
-// the sum-of-squares chains, thread 32 runs the walk, both out of shared memory; every other thread streams the weights in
-// (a chunk ahead, double buffered), divides them by the sum in parallel (the division is per element, not part of a chain)
-// and writes them back.  The walk starts together with the sum of squares, before N_eff is known, and its ancestors are
-// replaced by the identity when the filter does not resample.
+// ALL ranks.  Bit-exact ancestors need the reference's sequential fp64 order in three places: the sum, the sum of squares
+// and the cumulative sum c the walk compares against - each a chain of dependent additions (about 8 cycles an element on
+// this part) that no amount of parallelism shortens.  So the kernel makes sure the chains wait for nothing else, and that
+// nothing else is serial:
+//   * one CTA; thread 0 runs the sum and then the sum-of-squares chain, thread 32 the cumulative-sum chain next to it,
+//     both out of shared memory; every other thread streams the weights in (a chunk ahead, double buffered), divides them
+//     by the sum in parallel (the division is per element, not part of a chain) and writes them back;
+//   * the walk itself is NOT a chain: sample m takes the first i with U_m <= c_i (clamped to N - 1 when the weights run
+//     out).  c is non-decreasing (weights are products of positive likelihoods) and so is U_m = r + m / (N - 1), so the
+//     reference's nested loops (:484-497), which resume the search at the previous sample's i, find exactly that i - and
+//     every m can search for it independently (rbpf_ancestors_kernel, a binary search per sample over the stored c).
 constexpr int kPfMaxRanks = 64;
 constexpr int kNormThreads = 256;
 constexpr int kNormChunk = 2048;       // weights per buffer
 
-__global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
+__global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample r, int n_total)
 {
   __shared__ double buf[2][kNormChunk];
   __shared__ double s_sum;
-  __shared__ int s_resample;
   const int tid = threadIdx.x;
   const int n_chunks = (n_total + kNormChunk - 1) / kNormChunk;
   // chunk c into its buffer, by the `nload` threads that are not running a chain at the moment (lrank = 0 .. nload - 1)
@@ -1140,19 +1144,8 @@ __global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample
   if (tid == 0) s_sum = sum;
   __syncthreads();
   sum = s_sum;
-  // ---- w /= sum, sum of squares (:451-457, 463) and, side by side, the low-variance walk (:468-500) -------------------------
-  // Equivalent to the reference's nested loops: sample m takes the first i with U_m <= w_0 + ... + w_i, clamped to
-  // N - 1 when the weights run out.
-  double z = 0.0;
-  if (tid == 32) {
-    if (q.ext) z = q.ext[(size_t)q.ext_per];                               // caller passes a pointer to the last variate
-    else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
-  }
-  const double rr = z / (double)n_total;                                   // :475-476
-  const double step = 1.0 / (n_total - 1);
+  // ---- w /= sum; sum of squares (:451-457, 463) and, side by side, the cumulative sum of the walk (:481,492) ------------------
   double sq = 0.0, cacc = 0.0;
-  int m = 0;
-  double U = rr + (double)(m * step);                                      // :485
   load_chunk(0, true, sum, tid, kNormThreads);
   __syncthreads();
   for (int c = 0; c < n_chunks; c++) {
@@ -1167,20 +1160,17 @@ __global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample
       }
       for (; i < cnt; i++) { const double v = b[i]; sq += v * v; }
     } else if (tid == 32) {
-      for (int i = 0; i < cnt && m < n_total; i++) {
-        cacc += b[i];                                                      // c = w_0, then c += w_i (:481,492)
-        const int gi = c * kNormChunk + i;
-        if (gi == n_total - 1) {
-          // the weights are exhausted: every remaining sample clamps to N - 1 (:488-491)
-          while (m < n_total) { r.ancestors[m] = gi; m++; }
-          break;
-        }
-        while (m < n_total && !(U > cacc)) {
-          r.ancestors[m] = gi;
-          m++;
-          U = rr + (double)(m * step);
-        }
+      double *out = r.cum + (size_t)c * kNormChunk;
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        const double v0 = b[i], v1 = b[i + 1], v2 = b[i + 2], v3 = b[i + 3];
+        cacc += v0; const double c0 = cacc;                                // c = w_0, then c += w_i
+        cacc += v1; const double c1 = cacc;
+        cacc += v2; const double c2 = cacc;
+        cacc += v3;
+        out[i] = c0; out[i + 1] = c1; out[i + 2] = c2; out[i + 3] = cacc;
       }
+      for (; i < cnt; i++) { cacc += b[i]; out[i] = cacc; }
     } else if (c + 1 < n_chunks) {
       load_chunk(c + 1, true, sum, tid - (tid > 32 ? 2 : 1), kNormThreads - 2);
     }
@@ -1188,13 +1178,29 @@ __global__ void __launch_bounds__(kNormThreads) rbpf_normalize_kernel(PfResample
   }
   if (tid == 0) {
     const int neff = (int)(1.0 / sq);                                      // :463-464
-    const bool resample = neff < (n_total / 2);
-    r.info[0] = neff; r.info[1] = resample ? 1 : 0;
-    s_resample = resample ? 1 : 0;
+    r.info[0] = neff; r.info[1] = neff < (n_total / 2) ? 1 : 0;
   }
-  __syncthreads();
-  if (!s_resample)
-    for (int k = tid; k < n_total; k += kNormThreads) r.ancestors[k] = k;
+}
+
+// the ancestors: identity when the filter does not resample, else for every sample m the first i with U_m <= c_i
+__global__ void __launch_bounds__(256) rbpf_ancestors_kernel(PfResample r, int n_total, const __grid_constant__ PfCall q)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_total) return;
+  if (!r.info[1]) { r.ancestors[m] = m; return; }
+  double z;
+  if (q.ext) z = q.ext[(size_t)q.ext_per];                                 // caller passes a pointer to the last variate
+  else { double z1; normal_pair(q.seed_lo, q.seed_hi, kDomainRbpf, q.call, kStreamResample, 0u, z, z1); }
+  const double rr = z / (double)n_total;                                   // :475-476
+  const double step = 1.0 / (n_total - 1);
+  const double U = rr + (double)(m * step);                                // :485
+  // smallest i in [0, N - 1] with !(U > c_i); N - 1 when there is none (:486-491)
+  int lo = 0, hi = n_total - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (U > r.cum[mid]) lo = mid + 1; else hi = mid;
+  }
+  r.ancestors[m] = lo;
 }
 
 __global__ void rbpf_gather_weights_kernel(const PfParticle *meta, double *w, int n)
