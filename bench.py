@@ -633,15 +633,20 @@ def run_ours(args):
     launches = mppi.launchCount() - n0
 
     # ---- e2e: the public synchronous call, host pose in, host controls out ----------------------
+    # b2n_mppi_new_controls() = what controller::MPPI::newControls() of the C++ drop-in calls, `steps` times in a row, every
+    # call complete (controls on the host) before the next starts.  Timed twice: from a C loop inside the library (what a
+    # C++ node pays; the headline) and from this Python loop through ctypes (adds the interpreter's per-call cost).
+    barrier()
+    ms_c, v = mppi.timeNewControls(pose, args.steps)
+    barrier()
+    ms_e2e = max_over_ranks(ms_c * args.steps)
     barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
     for _ in range(args.steps):
         v = mppi.newControls(pose)
-    e1.record(stream)
-    barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    barrier()
+    ms_e2e_py = max_over_ranks(wall_ms)
 
     # ---- roofline pass: the rollout kernel alone, launched back to back between two CUDA events on the ------
     # handle's stream (event pairs around single launches add ~7 us of launch latency to a 20 us kernel)
@@ -671,7 +676,8 @@ def run_ours(args):
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, requested_exchange), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24,
-                    "d2h_bytes_per_step": 16,
+                    "d2h_bytes_per_step": 16, "caller": "C loop over b2n_mppi_new_controls (the C ABI the C++ drop-in class calls)",
+                    "python_ctypes_ms_per_step": ms_e2e_py / args.steps,
                     "note": "input is the 24-byte pose (travels as kernel parameters), output the 16-byte wheel command written by the call's kernel into mapped pinned memory (four 8-byte words, each tagged with the call's sequence number)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "mppi_rollout_kernel (rollout phase: loop + CTA partials, launched without the merger CTAs)", "achieved": achieved, "peak": peak, "unit": "GB/s",

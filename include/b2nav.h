@@ -134,6 +134,10 @@ int b2n_mppi_kernel_time(b2n_mppi *h, double *avg_ms, int *samples);
  * avg_ms = elapsed / launches */
 int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int launches, double *avg_ms);
 
+/* bench hook: `calls` synchronous b2n_mppi_new_controls() in a row from a C loop (host pose in, host controls out, every call
+ * complete before the next starts: what a C++ node's control loop pays), wall-clock mean in ms; the last controls in ul, ur */
+int b2n_mppi_time_new_controls(b2n_mppi *h, double x, double y, double theta, int calls, double *avg_ms, double *ul, double *ur);
+
 /* Sharded operation: every rank simulates its slice of the rollouts, the [T][6]
  * partials are exchanged with ONE ncclAllGather, every rank applies the identical update.
  * unique_id is the 128-byte ncclUniqueId made by b2n_comm_unique_id() on one rank and distributed

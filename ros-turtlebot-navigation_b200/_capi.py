@@ -81,6 +81,7 @@ PROTOTYPES = {
     "b2n_mppi_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "b2n_mppi_kernel_time": (C.c_int, [_vp, _P(D), _P(C.c_int)]),
     "b2n_mppi_time_rollout": (C.c_int, [_vp, D, D, D, C.c_int, _P(D)]),
+    "b2n_mppi_time_new_controls": (C.c_int, [_vp, D, D, D, C.c_int, _P(D), _P(D), _P(D)]),
     "b2n_comm_unique_id": (C.c_int, [_vp]),
     "b2n_mppi_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2n_mppi_p2p_export": (C.c_int, [_vp, C.c_int, _vp]),

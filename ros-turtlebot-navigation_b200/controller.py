@@ -174,6 +174,12 @@ class MPPI:
         _capi.check(self._lib.b2n_mppi_time_rollout(self._h, ps.x, ps.y, ps.theta, int(launches), C.byref(ms)))
         return ms.value
 
+    def timeNewControls(self, ps, calls):
+        """bench hook: mean wall-clock time (ms) of `calls` synchronous newControls() issued from a C loop, and the last controls"""
+        ms, ul, ur = C.c_double(), C.c_double(), C.c_double()
+        _capi.check(self._lib.b2n_mppi_time_new_controls(self._h, ps.x, ps.y, ps.theta, int(calls), C.byref(ms), C.byref(ul), C.byref(ur)))
+        return ms.value, WheelVelocities(ul.value, ur.value)
+
     def p2pExport(self, nranks):
         """allocate this rank's exchange area; returns the 64-byte CUDA IPC handle to hand to the other ranks"""
         buf = C.create_string_buffer(64)

@@ -846,6 +846,20 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
   return B2N_OK;
 }
 
+int b2n_mppi_time_new_controls(b2n_mppi *h, double x, double y, double theta, int calls, double *avg_ms, double *ul, double *ur)
+{
+  B2N_REQUIRE(h && avg_ms && calls > 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
+  double l = 0.0, r = 0.0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < calls; i++)
+    if (int rc = b2n_mppi_new_controls(h, x, y, theta, &l, &r)) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
+  *avg_ms = std::chrono::duration<double, std::milli>(t1 - t0).count() / calls;
+  if (ul) *ul = l;
+  if (ur) *ur = r;
+  return B2N_OK;
+}
+
 int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64)
 {
   B2N_REQUIRE(h && handle64, B2N_ERR_INVALID_ARGUMENT, "null argument");

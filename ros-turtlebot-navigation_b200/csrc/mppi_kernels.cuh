@@ -668,7 +668,9 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   const int warp = threadIdx.x >> 5;
   const int g = lane & (G - 1);    // position inside the rollout's lane group
   const int r = lane / G;          // which of the warp's R rollouts
-  const int gw = blockIdx.x * NW + warp;
+  // warp-major numbering of the grid's warps: the last, partly filled round of passes then spreads over ALL CTAs (the first
+  // warps of each) instead of filling the first CTAs - two CTAs share an SM, and an SM holding two full ones sets the pace
+  const int gw = warp * a.n_roll + (int)blockIdx.x;
   const int nw = a.n_roll * NW;
   const int T = FAST ? TP : a.T;
   const int t0 = g * S;            // first owned step
@@ -989,8 +991,10 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   // the rollouts are done: let the dependent grid (the next call) be scheduled while this CTA merges; it blocks in
   // griddepcontrol.wait until this whole grid has completed and the plan is visible
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (tma_store && lane == 0) tma_store_wait<0>();
-  __syncthreads();      // every warp has left the loop and drained its bulk stores: the staging rows are free
+  // the TMA unit has READ the staging rows (they are reused below); the writes themselves complete with the grid - a CTA
+  // does not have to sit out their latency
+  if (tma_store && lane == 0) tma_store_wait_read<0>();
+  __syncthreads();      // every warp has left the loop and its bulk stores have drained the staging rows
   mppi_stamp(a, 1);
 
   // ---- merge the CTA's accumulator sets per time step -----------------------------------------------------------------
