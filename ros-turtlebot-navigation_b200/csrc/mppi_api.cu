@@ -116,7 +116,7 @@ cudaError_t configure_shape(b2n_mppi *h)
   return cudaSuccess;
 }
 
-#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8) X(4, 16, 10) X(4, 16, 20) X(4, 32, 10) X(4, 32, 20)
+#define B2N_MPPI_SHAPES(X) X(2, 8, 8) X(4, 8, 8) X(2, 16, 8) X(4, 16, 8) X(2, 32, 8) X(4, 32, 8) X(8, 32, 8) X(4, 16, 10) X(4, 16, 12) X(4, 16, 20) X(4, 32, 10) X(4, 32, 20)
 
 cudaError_t configure(b2n_mppi *h)
 {
@@ -160,8 +160,8 @@ void pick_shape(int T, int &S, int &G, int &NW)
   NW = 8;
   if (T <= 16) { S = 2; G = 8; }
   else if (T <= 32) { S = 4; G = 8; }
-  else if (T <= 64) { S = 4; G = 16; NW = 10; }      // 2 CTAs x 10 warps per SM at 96 registers: 20 warps, no spill traffic in the loop,
-  else if (T <= 128) { S = 4; G = 32; NW = 10; }     //   and K = 16384 divides into 2.8 passes per warp (8-warp CTAs: 2.3, a third pass for a third of them)
+  else if (T <= 64) { S = 4; G = 16; NW = 10; }      // 2 CTAs x 10 warps per SM at 96 registers: 20 warps, no spill traffic in the loop
+  else if (T <= 128) { S = 4; G = 32; NW = 10; }     //   (measured at C2: 12 warps x 2 at 80 registers 23.7 us per call, 13 x 2 at 72: 26.2, 10 x 2: 20.9)
   else { S = 8; G = 32; }
   if (const char *env = std::getenv("B2N_MPPI_SHAPE")) {
     int s = 0, g = 0, w = 8;

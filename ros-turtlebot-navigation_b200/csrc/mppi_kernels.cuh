@@ -614,7 +614,7 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
 }
 
 // dynamic shared memory of the rollout kernel:
-//   [warps][2][32*S*3] fp32 staging rows of the state tensor (after the loop: merge scratch, [threads*6] doubles)
+//   [warps][1 or 2][32*S*3] fp32 staging rows of the state tensor (after the loop: merge scratch, [threads*6] doubles)
 //   [S*4][threads]     fp64 online-softmax accumulators (min J, sum e, sum e*duL, sum e*duR) per owned step
 //   [S/2][threads]     float4 sums of the binary32 variates (sum duL, sum duR before the scaling by sigma)
 //   [2][G*S]           the control plan
@@ -623,9 +623,12 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
 //   [S*2][threads]     fp64 sum duL / sum duR (generic variant only)
 //   [tile][tile]       fp32 obstacle-field tile (obstacle variants only)
 __host__ __device__ constexpr size_t mppi_dz_bytes(int S) { return (size_t)S * 8; }
+// staging buffers per warp: ONE (a pass is microseconds, the TMA unit drains a row in a fraction of that: the wait before the
+// next pass's first store is over by then) - except where one buffer would be smaller than the merge scratch that reuses it
+__host__ __device__ constexpr int mppi_stage_buffers(int S) { return S >= 4 ? 1 : 2; }
 __host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW, bool obs, bool fast)
 {
-  return (size_t)NW * 2 * 32 * S * 3 * sizeof(float) + (size_t)S * 4 * NW * 32 * sizeof(double) + (size_t)NW * 32 * mppi_dz_bytes(S) +
+  return (size_t)NW * mppi_stage_buffers(S) * 32 * S * 3 * sizeof(float) + (size_t)S * 4 * NW * 32 * sizeof(double) + (size_t)NW * 32 * mppi_dz_bytes(S) +
          (size_t)2 * G * S * sizeof(double) + (fast ? (size_t)NW * 32 * S * (sizeof(double) + sizeof(float2)) : (size_t)S * 2 * NW * 32 * sizeof(double)) +
          (obs ? (size_t)kMppiObsTile * kMppiObsTile * sizeof(float) + 16 : 0);
 }
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   }
   constexpr int R = 32 / G;        // rollouts a warp carries at a time
   constexpr int TP = G * S;        // padded horizon
-  constexpr int NBUF = 2;
+  constexpr int NBUF = mppi_stage_buffers(S);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr size_t kStageBytes = (size_t)NW * NBUF * 32 * S * 3 * 4, kAccBytes = (size_t)S * 4 * NT * 8, kDzBytes = (size_t)NT * mppi_dz_bytes(S),
                    kPlanBytes = (size_t)2 * TP * 8, kDaccBytes = FAST ? (size_t)NT * S * 16 : (size_t)S * 2 * NT * 8;
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   }
   int buf = 0;
   bool have_noise = true;
-  for (; base < a.K; base += nw * R, buf ^= 1) {
+  for (; base < a.K; base += nw * R, buf ^= (NBUF - 1)) {
     const int k = base + r;
     const bool live = k < a.K;
     const bool first = base == gw * R + nw * R;      // (the SECOND pass: thresholds set, steady state)

@@ -16,7 +16,7 @@ params = sys.argv[4] if len(sys.argv) > 4 else "shipped"
 pkg = _pkg.load()
 orc = pkg.synthetic          # shipped parameters and synthetic inputs (plain numpy)
 prm = orc.SHIPPED if params == "shipped" else orc.MILD
-shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8), (4, 16, 10), (4, 16, 20), (4, 32, 20)]
+shapes = [(2, 8, 8), (4, 8, 8), (2, 16, 8), (4, 16, 8), (2, 32, 8), (4, 32, 8), (8, 32, 8), (4, 16, 10), (4, 16, 12), (4, 16, 20), (4, 32, 10), (4, 32, 20)]
 if os.environ.get("PROBE_SHAPES"):
     shapes = [tuple(int(v) for v in x.split(",")) for x in os.environ["PROBE_SHAPES"].split(";")]
 for shape in shapes:
