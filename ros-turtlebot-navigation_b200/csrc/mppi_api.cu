@@ -95,9 +95,9 @@ cudaError_t configure_shape(b2n_mppi *h)
   h->smem = mppi_rollout_smem(S, G, NW, true, false);
   cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, false, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mppi_rollout_smem(S, G, NW, false, true));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  e = cudaFuncSetAttribute(mppi_rollout_kernel<S, G, true, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mppi_rollout_smem(S, G, NW, true, true));
   if (e != cudaSuccess) return e;
   int per_sm = 0, per_sm_fast = 0, per_sm_obs = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel<S, G, false, false, NW>, NW * 32, h->smem);

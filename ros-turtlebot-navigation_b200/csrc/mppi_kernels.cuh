@@ -615,21 +615,26 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
 
 // dynamic shared memory of the rollout kernel:
 //   [warps][1 or 2][32*S*3] fp32 staging rows of the state tensor (after the loop: merge scratch, [threads*6] doubles)
-//   [S*4][threads]     fp64 online-softmax accumulators (min J, sum e, sum e*duL, sum e*duR) per owned step
+//   [S*4][threads]     online-softmax accumulators (min J, sum e, sum e*duL, sum e*duR) per owned step: fp64 (generic), or fp64 min +
+//                      three binary32 sums (production)
 //   [S/2][threads]     float4 sums of the binary32 variates (sum duL, sum duR before the scaling by sigma)
 //   [2][G*S]           the control plan
-//   [warps][32*S]      fp64 cost-to-go and float2 variates of the rollouts in flight, for the transposition in front of the
-//                      softmax (production variants)
+//   [warps][3][32*S]   fp64 cost-to-go of the last passes' rollouts, by step: the softmax accumulators are updated in
+//                      batches (production variants)
 //   [S*2][threads]     fp64 sum duL / sum duR (generic variant only)
 //   [tile][tile]       fp32 obstacle-field tile (obstacle variants only)
+// accumulator set of one step in shared memory: generic (min J, sum e, sum e*duL, sum e*duR) fp64; production min J fp64 and the
+// three sums binary32 (a lane's set holds a few rollouts: 1e-7 relative, merged in fp64 from the CTA level on)
+__host__ __device__ constexpr size_t mppi_acc_bytes(bool fast) { return fast ? 8 + 3 * 4 : 4 * 8; }
+constexpr int kMppiBatch = 3;        // passes whose cost-to-go is buffered before the softmax accumulators are touched (production variants)
 __host__ __device__ constexpr size_t mppi_dz_bytes(int S) { return (size_t)S * 8; }
 // staging buffers per warp: ONE (a pass is microseconds, the TMA unit drains a row in a fraction of that: the wait before the
 // next pass's first store is over by then) - except where one buffer would be smaller than the merge scratch that reuses it
 __host__ __device__ constexpr int mppi_stage_buffers(int S) { return S >= 4 ? 1 : 2; }
 __host__ __device__ constexpr size_t mppi_rollout_smem(int S, int G, int NW, bool obs, bool fast)
 {
-  return (size_t)NW * mppi_stage_buffers(S) * 32 * S * 3 * sizeof(float) + (size_t)S * 4 * NW * 32 * sizeof(double) + (size_t)NW * 32 * mppi_dz_bytes(S) +
-         (size_t)2 * G * S * sizeof(double) + (fast ? (size_t)NW * 32 * S * (sizeof(double) + sizeof(float2)) : (size_t)S * 2 * NW * 32 * sizeof(double)) +
+  return (size_t)NW * mppi_stage_buffers(S) * 32 * S * 3 * sizeof(float) + (size_t)S * NW * 32 * mppi_acc_bytes(fast) + (size_t)NW * 32 * mppi_dz_bytes(S) +
+         (size_t)2 * G * S * sizeof(double) + (fast ? (size_t)kMppiBatch * NW * 32 * S * sizeof(double) : (size_t)S * 2 * NW * 32 * sizeof(double)) +
          (obs ? (size_t)kMppiObsTile * kMppiObsTile * sizeof(float) + 16 : 0);
 }
 // CTAs per SM the register budget is cut for: 8-warp CTAs run three to an SM (80 registers), 10-warp CTAs two and 20-warp CTAs
@@ -652,8 +657,8 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   constexpr int TP = G * S;        // padded horizon
   constexpr int NBUF = mppi_stage_buffers(S);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr size_t kStageBytes = (size_t)NW * NBUF * 32 * S * 3 * 4, kAccBytes = (size_t)S * 4 * NT * 8, kDzBytes = (size_t)NT * mppi_dz_bytes(S),
-                   kPlanBytes = (size_t)2 * TP * 8, kDaccBytes = FAST ? (size_t)NT * S * 16 : (size_t)S * 2 * NT * 8;
+  constexpr size_t kStageBytes = (size_t)NW * NBUF * 32 * S * 3 * 4, kAccBytes = (size_t)S * NT * mppi_acc_bytes(FAST), kDzBytes = (size_t)NT * mppi_dz_bytes(S),
+                   kPlanBytes = (size_t)2 * TP * 8, kDaccBytes = FAST ? (size_t)kMppiBatch * NT * S * 8 : (size_t)S * 2 * NT * 8;
   static_assert((size_t)NT * 48 <= kStageBytes, "the merge scratch lives in the staging rows");
   float *stage_base = reinterpret_cast<float *>(smem_raw);                                       // [warps][2][R*TP*3]
   double *scratch = reinterpret_cast<double *>(smem_raw);                                        // [NT*6], after the loop
@@ -662,8 +667,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   float4 *dz4 = reinterpret_cast<float4 *>(smem_raw + kStageBytes + kAccBytes);                  // [S/2][threads]
   double *plan = reinterpret_cast<double *>(smem_raw + kStageBytes + kAccBytes + kDzBytes);      // [2][TP]
   double *dacc = reinterpret_cast<double *>(smem_raw + kStageBytes + kAccBytes + kDzBytes + kPlanBytes);     // [S*2][threads], generic only
-  double *jbuf = dacc;                                                                                      // [warps][R][TP], production only
-  float2 *zsm = reinterpret_cast<float2 *>(jbuf + (size_t)NW * R * TP);                                     // [warps][R][TP] (zL, zR), production only
+  double *jbuf = dacc;                                                                                      // [warps][kMppiBatch][R][TP], production only
   float *tile = reinterpret_cast<float *>(smem_raw + kStageBytes + kAccBytes + kDzBytes + kPlanBytes + kDaccBytes);
   uint64_t *tile_bar = reinterpret_cast<uint64_t *>(tile + kMppiObsTile * kMppiObsTile);
 
@@ -686,11 +690,18 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
 
   // online-softmax accumulators of this lane's steps: (min J, sum e, sum e*duL, sum e*duR) x S in shared memory, with
   // the high word of (min J + cut) in a register: a cost-to-go above it cannot contribute
+  float *accf = reinterpret_cast<float *>(acc_base + (size_t)S * NT) + threadIdx.x;      // production: [S*3][threads] behind the [S] minima
 #pragma unroll
   for (int s = 0; s < S; s++) {
-    acc[(s * 4 + 0) * NT] = inf;
+    if (FAST) {
+      acc[s * NT] = inf;
 #pragma unroll
-    for (int j = 1; j < 4; j++) acc[(s * 4 + j) * NT] = 0.0;
+      for (int j = 0; j < 3; j++) accf[(s * 3 + j) * NT] = 0.f;
+    } else {
+      acc[(s * 4 + 0) * NT] = inf;
+#pragma unroll
+      for (int j = 1; j < 4; j++) acc[(s * 4 + j) * NT] = 0.0;
+    }
   }
   int thr_hi[S];
   // sum duL, sum duR take part in the update only through the +1e-8 weight floor (mppi.cpp:117): the production variant
@@ -748,6 +759,61 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   if (obs_on && a.obs_ti0 >= 0) mbar_wait(tile_bar, 0);
 
   mppi_stamp(a, 0);
+  // ---- production variants: the T softmaxes in BATCHES -------------------------------------------------------------------
+  // A lane's accumulator set sees only K / (warps x R) rollouts per call (2.8 at C2): updated rollout by rollout, most
+  // updates are "a new minimum of a nearly empty set" - a serialised, branchy block per owned step and pass, with the
+  // warp walking through all of them because some lane always needs each.  Instead the cost-to-go of kMppiBatch passes is
+  // parked in shared memory BY STEP (which also transposes it: lane g simulated steps gS .. gS + S - 1 but keeps the
+  // accumulators of steps g, G + g, 2G + g, ...), and the set is then updated once per batch: minimum over the old set and
+  // the candidates first, every exponential independent of the others, straight-line code for all lanes.  The variates of
+  // the candidates are read again from the buffer the noise kernel filled (L1 / L2 hits).
+  int nb = 0;
+  int kb[kMppiBatch];
+#pragma unroll
+  for (int p = 0; p < kMppiBatch; p++) kb[p] = 0;
+  auto flush = [&](int np) {
+    __syncwarp();
+    const double *jb = jbuf + (size_t)warp * kMppiBatch * R * TP + (size_t)r * TP;
+    const double k2 = a.inv_lambda * 1.4426950408889634;       // weights as 2^((M - J) k2)
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int ts = s * G + g;                       // the step this accumulator set belongs to
+      const double m0 = acc[s * NT];
+      const float S0 = accf[(s * 3) * NT], A0 = accf[(s * 3 + 1) * NT], B0 = accf[(s * 3 + 2) * NT];
+      double Jc[kMppiBatch];
+      float2 zc[kMppiBatch];
+#pragma unroll
+      for (int p = 0; p < kMppiBatch; p++) {
+        const int kk = kb[p] + r;
+        const bool on = p < np && kk < a.K;
+        Jc[p] = on ? jb[(size_t)p * R * TP + ts] : inf;
+        const float4 q = __ldg(a.zbuf + ((size_t)(on ? kk : 0) * (TP / 2) + (ts >> 1)));
+        zc[p] = (g & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+      }
+      double M = m0;
+#pragma unroll
+      for (int p = 0; p < kMppiBatch; p++) M = fmin(M, Jc[p]);
+      // weight of a member = 2^((M - J) k2) through the SFU in binary32: the exponent difference is formed in fp64 (that is
+      // where the conditioning sits), the weight itself needs the 1e-5 of the contract, not 1e-16.  A member that is not
+      // there (J = +inf) gets 2^-inf = 0, weights below 2^-126 flush to zero: no branch anywhere.  (All absent: M = +inf
+      // would give inf - inf; the reference point is then irrelevant.)
+      const double Mr = (M == inf) ? 0.0 : M;
+      float f0;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f0) : "f"((float)((Mr - m0) * k2)));
+      float Sn = S0 * f0, An = A0 * f0, Bn = B0 * f0;
+#pragma unroll
+      for (int p = 0; p < kMppiBatch; p++) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((float)((Mr - Jc[p]) * k2)));
+        Sn += e;
+        An = fmaf(e, zc[p].x, An);
+        Bn = fmaf(e, zc[p].y, Bn);
+      }
+      acc[s * NT] = M;
+      accf[(s * 3) * NT] = Sn; accf[(s * 3 + 1) * NT] = An; accf[(s * 3 + 2) * NT] = Bn;
+    }
+    __syncwarp();
+  };
   float4 zn[FAST ? S / 2 : 1];
   if (z_ahead && base < a.K) {
     const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
@@ -777,12 +843,6 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     }
     have_noise = false;
     mppi_clock(a, first, 9);
-    if (FAST) {
-      // the rollout's variates by step, for the lanes that keep the steps' accumulators (softmax below)
-      float4 *zrow = reinterpret_cast<float4 *>(zsm + (size_t)(warp * R + r) * TP + t0);
-#pragma unroll
-      for (int s = 0; s < S; s += 2) zrow[s / 2] = make_float4(zq[2 * s], zq[2 * s + 1], zq[2 * s + 2], zq[2 * s + 3]);
-    }
     if (FAST && live) {
 #pragma unroll
       for (int s = 0; s < S; s += 2) {
@@ -908,66 +968,51 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     const double ej = shift1<G, false>(ij, 0.0);
 
     mppi_clock(a, first, 16);
-    // ---- online softmax over rollouts, one accumulator set per step ---------------------------------------------------
-    // Production variants TRANSPOSE first: lane g simulated steps gS .. gS + S - 1, but keeps the accumulators of steps
-    // g, G + g, 2G + g, ...  Which steps of the horizon are "soft" (many rollouts within the exponent range of the
-    // minimum) depends on the step, not on the rollout: with the simulation's ownership they all sit in one or two lanes
-    // of a group and the warp walks through every one of its S accumulator blocks for them; transposed they share one
-    // slot across the lanes and the other blocks are skipped by the whole warp.
-    double Jt[S];
+    // ---- the T softmaxes over rollouts (mppi.cpp:112-121), carried online -------------------------------------------------
     if (FAST) {
-      double *jb = jbuf + (size_t)(warp * R + r) * TP;
+      // park this pass's cost-to-go by step; the accumulators are updated once per kMppiBatch passes (flush above)
+      double *jb = jbuf + ((size_t)(warp * kMppiBatch + nb) * R + r) * TP;
 #pragma unroll
       for (int s = 0; s < S; s += 2) *reinterpret_cast<double2 *>(jb + t0 + s) = make_double2(J[s] + ej, J[s + 1] + ej);
-      __syncwarp();
 #pragma unroll
-      for (int s = 0; s < S; s++) Jt[s] = jb[s * G + g];
-      __syncwarp();
+      for (int p = 0; p < kMppiBatch; p++)
+        if (nb == p) kb[p] = base;
+      nb++;
+      if (nb == kMppiBatch) { flush(nb); nb = 0; }
     } else {
 #pragma unroll
-      for (int s = 0; s < S; s++) Jt[s] = J[s] + ej;
-    }
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const double Js = Jt[s];
-      const int ts = FAST ? s * G + g : t0 + s;      // the step this accumulator set belongs to
-      if (live && (FAST || ts < T)) {
-        if (!FAST) { sDL[s] += duL[s]; sDR[s] += duR[s]; }
-        // J >= 0, so the high words order like the values: one integer compare against the register threshold decides
-        // whether this rollout can matter for the step (at the shipped temperature it rarely does)
-        if (__double2hiint(Js) <= thr_hi[s]) {
-          double *c = acc + s * 4 * NT;
-          const double m0 = c[0];
-          const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
-          const bool newmin = d > 0.0;
-          const double e = mppi_exp_neg<FAST>(-fabs(d));
-          if (newmin || e != 0.0) {
-            double l, rr;
-            if (FAST) {
-              // the step's perturbation, re-derived from its variates (left in shared memory by the simulating lane)
-              const float2 q = zsm[(size_t)(warp * R + r) * TP + ts];
-              l = (double)q.x * a.sigL;
-              rr = (double)q.y * a.sigR;
-            } else {
-              l = duL[s]; rr = duR[s];
-            }
-            if (newmin) {
-              // (rare) the sums are rescaled to the new minimum
-              c[NT] = fma(c[NT], e, 1.0);
-              c[2 * NT] = fma(c[2 * NT], e, l);
-              c[3 * NT] = fma(c[3 * NT], e, rr);
-              c[0] = Js;
-              if (a.thr_on) thr_hi[s] = __double2hiint(Js + a.cut_lambda) + 1;
-            } else {
-              c[NT] += e;
-              c[2 * NT] = fma(e, l, c[2 * NT]);
-              c[3 * NT] = fma(e, rr, c[3 * NT]);
+      for (int s = 0; s < S; s++) {
+        const double Js = J[s] + ej;
+        if (live && t0 + s < T) {
+          sDL[s] += duL[s]; sDR[s] += duR[s];
+          // J >= 0, so the high words order like the values: one integer compare against the register threshold decides
+          // whether this rollout can matter for the step
+          if (__double2hiint(Js) <= thr_hi[s]) {
+            double *c = acc + s * 4 * NT;
+            const double m0 = c[0];
+            const double d = (m0 - Js) * a.inv_lambda;     // > 0: J is the new minimum
+            const bool newmin = d > 0.0;
+            const double e = mppi_exp_neg<false>(-fabs(d));
+            if (newmin || e != 0.0) {
+              const double l = duL[s], rr = duR[s];
+              if (newmin) {
+                // the sums are rescaled to the new minimum
+                c[NT] = fma(c[NT], e, 1.0);
+                c[2 * NT] = fma(c[2 * NT], e, l);
+                c[3 * NT] = fma(c[3 * NT], e, rr);
+                c[0] = Js;
+                if (a.thr_on) thr_hi[s] = __double2hiint(Js + a.cut_lambda) + 1;
+              } else {
+                c[NT] += e;
+                c[2 * NT] = fma(e, l, c[2 * NT]);
+                c[3 * NT] = fma(e, rr, c[3 * NT]);
+              }
             }
           }
-        }
-        if (capture) {
-          a.J_out[(size_t)k * T + t0 + s] = Js;
-          reinterpret_cast<double2 *>(a.du_out)[(size_t)k * T + t0 + s] = make_double2(duL[s], duR[s]);
+          if (capture) {
+            a.J_out[(size_t)k * T + t0 + s] = Js;
+            reinterpret_cast<double2 *>(a.du_out)[(size_t)k * T + t0 + s] = make_double2(duL[s], duR[s]);
+          }
         }
       }
     }
@@ -991,6 +1036,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     }
     mppi_clock(a, first, 18);
   }
+  if (FAST && nb) flush(nb);
   // the rollouts are done: let the dependent grid (the next call) be scheduled while this CTA merges; it blocks in
   // griddepcontrol.wait until this whole grid has completed and the plan is visible
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1017,16 +1063,21 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   // variants lane t mod G holds them in slot t / G (transposed, see the softmax above), the sums of the variates stay with
   // the lane that simulated the step (lane t / S, slot t mod S)
   auto grp = [&](int i) { return (i / R) * 32 + (i % R) * G; };
-  auto cta_min = [&](int t, int i) { return FAST ? acc_base[((t / G) * 4) * NT + grp(i) + t % G] : acc_base[((t % S) * 4) * NT + grp(i) + t / S]; };
+  const float *accf_base = reinterpret_cast<const float *>(acc_base + (size_t)S * NT);
+  auto cta_min = [&](int t, int i) { return FAST ? acc_base[(t / G) * NT + grp(i) + t % G] : acc_base[((t % S) * 4) * NT + grp(i) + t / S]; };
   auto cta_set = [&](int t, int i, double v[6]) {
-    const int tid_a = grp(i) + (FAST ? t % G : t / S), sa = FAST ? t / G : t % S;
     const int tid_d = grp(i) + t / S, sd = t % S;
-#pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = acc_base[(sa * 4 + j) * NT + tid_a];
     if (FAST) {
+      const int tid_a = grp(i) + t % G, sa = t / G;
+      v[0] = acc_base[sa * NT + tid_a];
+      v[1] = (double)accf_base[(sa * 3) * NT + tid_a];
+      v[2] = (double)accf_base[(sa * 3 + 1) * NT + tid_a] * a.sigL;       // the sums were taken over the variates
+      v[3] = (double)accf_base[(sa * 3 + 2) * NT + tid_a] * a.sigR;
       const float2 z = reinterpret_cast<const float2 *>(dz4 + (sd / 2) * NT + tid_d)[sd & 1];
       v[4] = (double)z.x * a.sigL; v[5] = (double)z.y * a.sigR;
     } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = acc_base[(sd * 4 + j) * NT + tid_d];
       v[4] = dacc[(sd * 2) * NT + tid_d]; v[5] = dacc[(sd * 2 + 1) * NT + tid_d];
     }
   };
