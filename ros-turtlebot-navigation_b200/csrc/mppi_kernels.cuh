@@ -197,114 +197,42 @@ __device__ __forceinline__ void mppi_sincos_small(const MppiArgs &a, double d, d
 }
 
 // ---- segmented warp scans over the G lanes of a rollout -----------------------------------------------------------
-// shfl.sync returns, next to the value, whether the source lane was inside the segment; the dependent arithmetic is
-// predicated on it directly (the C++ intrinsics drop that predicate, and `if (g >= d)` costs a compare plus two
-// selects per double).
+// (Plain shuffles and selects.  A version that took shfl.sync's "source lane in range" predicate and predicated the
+// dependent fp64 arithmetic on it in inline PTX was built and measured: ptxas turns the predicated fp64 operations back
+// into FSEL pairs on the 32-bit halves and the unpack / repack around the asm costs a hundred register moves per pass.)
 template <int G>
-__device__ __forceinline__ void scan_rot_up(double &tc, double &ts, double &tth, int d)
+__device__ __forceinline__ void scan_rot_up(double &tc, double &ts, double &tth, int d, int g)
 {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b32 a0, a1, b0, b1, c0, c1;\n\t"
-      ".reg .f64 oc, os, ot, m0, m1;\n\t"
-      "mov.b64 {a0, a1}, %0;\n\t"
-      "mov.b64 {b0, b1}, %1;\n\t"
-      "mov.b64 {c0, c1}, %2;\n\t"
-      "shfl.sync.up.b32 a0|p, a0, %3, %4, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 a1, a1, %3, %4, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 b0, b0, %3, %4, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 b1, b1, %3, %4, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 c0, c0, %3, %4, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 c1, c1, %3, %4, 0xffffffff;\n\t"
-      "mov.b64 oc, {a0, a1};\n\t"
-      "mov.b64 os, {b0, b1};\n\t"
-      "mov.b64 ot, {c0, c1};\n\t"
-      "@p mul.f64 m0, %1, os;\n\t"            // ts * os
-      "@p mul.f64 m1, %1, oc;\n\t"            // ts * oc
-      "@p neg.f64 m0, m0;\n\t"
-      "@p fma.rn.f64 m0, %0, oc, m0;\n\t"     // tc * oc - ts * os
-      "@p fma.rn.f64 %1, %0, os, m1;\n\t"     // tc * os + ts * oc
-      "@p mov.f64 %0, m0;\n\t"
-      "@p add.f64 %2, %2, ot;\n\t"
-      "}"
-      : "+d"(tc), "+d"(ts), "+d"(tth)
-      : "r"(d), "n"((32 - G) << 8));
+  const double oc = __shfl_up_sync(kFullMask, tc, d, G), os = __shfl_up_sync(kFullMask, ts, d, G);
+  const double ot = __shfl_up_sync(kFullMask, tth, d, G);
+  if (g >= d) {
+    const double nc = fma(tc, oc, -(ts * os));
+    ts = fma(tc, os, ts * oc);
+    tc = nc;
+    tth += ot;
+  }
 }
 
 template <int G>
-__device__ __forceinline__ void scan_add2_up(double &x, double &y, int d)
+__device__ __forceinline__ void scan_add2_up(double &x, double &y, int d, int g)
 {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b32 a0, a1, b0, b1;\n\t"
-      ".reg .f64 ox, oy;\n\t"
-      "mov.b64 {a0, a1}, %0;\n\t"
-      "mov.b64 {b0, b1}, %1;\n\t"
-      "shfl.sync.up.b32 a0|p, a0, %2, %3, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 a1, a1, %2, %3, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 b0, b0, %2, %3, 0xffffffff;\n\t"
-      "shfl.sync.up.b32 b1, b1, %2, %3, 0xffffffff;\n\t"
-      "mov.b64 ox, {a0, a1};\n\t"
-      "mov.b64 oy, {b0, b1};\n\t"
-      "@p add.f64 %0, %0, ox;\n\t"
-      "@p add.f64 %1, %1, oy;\n\t"
-      "}"
-      : "+d"(x), "+d"(y)
-      : "r"(d), "n"((32 - G) << 8));
+  const double ox = __shfl_up_sync(kFullMask, x, d, G), oy = __shfl_up_sync(kFullMask, y, d, G);
+  if (g >= d) { x += ox; y += oy; }
 }
 
 template <int G>
-__device__ __forceinline__ void scan_add_down(double &x, int d)
+__device__ __forceinline__ void scan_add_down(double &x, int d, int g)
 {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b32 a0, a1;\n\t"
-      ".reg .f64 ox;\n\t"
-      "mov.b64 {a0, a1}, %0;\n\t"
-      "shfl.sync.down.b32 a0|p, a0, %1, %2, 0xffffffff;\n\t"
-      "shfl.sync.down.b32 a1, a1, %1, %2, 0xffffffff;\n\t"
-      "mov.b64 ox, {a0, a1};\n\t"
-      "@p add.f64 %0, %0, ox;\n\t"
-      "}"
-      : "+d"(x)
-      : "r"(d), "n"(((32 - G) << 8) | 0x1f));
+  const double ox = __shfl_down_sync(kFullMask, x, d, G);
+  if (g + d < G) x += ox;
 }
 
 // value of the neighbouring lane inside the segment (delta 1), or `edge` at the segment boundary
 template <int G, bool UP>
-__device__ __forceinline__ double shift1(double v, double edge)
+__device__ __forceinline__ double shift1(double v, double edge, int g)
 {
-  double o;
-  if (UP)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 a0, a1;\n\t"
-        "mov.b64 {a0, a1}, %1;\n\t"
-        "shfl.sync.up.b32 a0|p, a0, 1, %3, 0xffffffff;\n\t"
-        "shfl.sync.up.b32 a1, a1, 1, %3, 0xffffffff;\n\t"
-        "mov.b64 %0, {a0, a1};\n\t"
-        "@!p mov.f64 %0, %2;\n\t"
-        "}"
-        : "=d"(o)
-        : "d"(v), "d"(edge), "n"((32 - G) << 8));
-  else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 a0, a1;\n\t"
-        "mov.b64 {a0, a1}, %1;\n\t"
-        "shfl.sync.down.b32 a0|p, a0, 1, %3, 0xffffffff;\n\t"
-        "shfl.sync.down.b32 a1, a1, 1, %3, 0xffffffff;\n\t"
-        "mov.b64 %0, {a0, a1};\n\t"
-        "@!p mov.f64 %0, %2;\n\t"
-        "}"
-        : "=d"(o)
-        : "d"(v), "d"(edge), "n"(((32 - G) << 8) | 0x1f));
-  return o;
+  const double o = UP ? __shfl_up_sync(kFullMask, v, 1, G) : __shfl_down_sync(kFullMask, v, 1, G);
+  return (UP ? g == 0 : g == G - 1) ? edge : o;
 }
 
 // ---- noise ----------------------------------------------------------------------------------------------------------
@@ -893,10 +821,10 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     mppi_clock(a, first, 11);
     // ---- segmented inclusive scans over the rollout's G lanes: rotation product and heading sum ----------
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) scan_rot_up<G>(tc, ts, tth, d);
+    for (int d = 1; d < G; d <<= 1) scan_rot_up<G>(tc, ts, tth, d, g);
     // exclusive prefix, seeded with the start heading: the world heading at the lane's first step
-    double rc = shift1<G, true>(tc, 1.0), rs = shift1<G, true>(ts, 0.0);
-    const double th = shift1<G, true>(tth, 0.0) + a.x0[2];
+    double rc = shift1<G, true>(tc, 1.0, g), rs = shift1<G, true>(ts, 0.0, g);
+    const double th = shift1<G, true>(tth, 0.0, g) + a.x0[2];
     {
       const double nc = fma(rc, cos0, -(rs * sin0));
       rs = fma(rc, sin0, rs * cos0);
@@ -907,8 +835,8 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     // ---- position: the lane's displacement turned into the world frame, segmented prefix sums ----------------------
     double ix = fma(rc, ax, -(rs * ay)), iy = fma(rs, ax, rc * ay);
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) scan_add2_up<G>(ix, iy, d);
-    const double ex = shift1<G, true>(ix, 0.0) + a.x0[0], ey = shift1<G, true>(iy, 0.0) + a.x0[1];
+    for (int d = 1; d < G; d <<= 1) scan_add2_up<G>(ix, iy, d, g);
+    const double ex = shift1<G, true>(ix, 0.0, g) + a.x0[0], ey = shift1<G, true>(iy, 0.0, g) + a.x0[1];
 
     mppi_clock(a, first, 13);
     // ---- states after each step -> staging row; loss (mppi.cpp:99-105, mppi.hpp:87-105) -------------------
@@ -964,8 +892,8 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     // ---- cost-to-go: segmented suffix sum over the lanes ---------------------------------------------------
     double ij = rj;
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) scan_add_down<G>(ij, d);
-    const double ej = shift1<G, false>(ij, 0.0);
+    for (int d = 1; d < G; d <<= 1) scan_add_down<G>(ij, d, g);
+    const double ej = shift1<G, false>(ij, 0.0, g);
 
     mppi_clock(a, first, 16);
     // ---- the T softmaxes over rollouts (mppi.cpp:112-121), carried online -------------------------------------------------
