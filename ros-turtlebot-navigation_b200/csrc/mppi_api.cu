@@ -248,7 +248,7 @@ void arm_tail(b2n_mppi *h, MppiArgs &a)
   a.out_seq = reinterpret_cast<unsigned long long *>(h->d_out_host + 2);
   a.dbg = h->d_dbg;
   a.seq = ++h->out_seq;
-  a.stepstats = h->d_stepstats;
+  a.stepstats = h->capture ? h->d_stepstats : nullptr;      // the weights tap needs them; a production call skips the stores
   a.merged = h->d_merged;
   a.rank = 0; a.nranks = 1;
   if (h->nranks > 1 && h->p2p_ready) {

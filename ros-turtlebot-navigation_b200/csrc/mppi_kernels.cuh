@@ -110,6 +110,9 @@ struct MppiUpdateArgs
   double *merged;          // [T][6] when merge_only
 };
 
+// minimum of two costs (never NaN): a compare and a select, where fmin spends half a dozen instructions on NaN rules
+__device__ __forceinline__ double mppi_min(double a, double b) { return b < a ? b : a; }
+
 constexpr int kMppiObsTile = 32;             // cells per side of the obstacle-field tile staged through TMA
 
 // cell index of a coordinate exactly as the oracle computes it, floor((x - xmin) / res): the rare path of
@@ -253,10 +256,16 @@ __device__ __forceinline__ void mppi_normal_quad(const MppiArgs &a, uint32_t str
 }
 
 constexpr int kMppiDbgSlots = 24;
-// SM clock of warp 0 at a point inside its first pass (slots 8 and up)
+// SM clock of warp 0 at a point inside its second pass (slots 8 and up).  Compiled in only with -DB2N_MPPI_PHASE_CLOCKS (the
+// tuning build behind the phase table of DESIGN.md 3.3): eleven predicated stores and clock reads per pass otherwise sit in
+// the issue-bound loop of every call.
 __device__ __forceinline__ void mppi_clock(const MppiArgs &a, bool first, int j)
 {
+#ifdef B2N_MPPI_PHASE_CLOCKS
   if (a.dbg && first && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + j] = (unsigned long long)clock64();
+#else
+  (void)a; (void)first; (void)j;
+#endif
 }
 
 __device__ __forceinline__ void mppi_stamp(const MppiArgs &a, int j)
@@ -290,13 +299,13 @@ __device__ __forceinline__ void mppi_merge_sets(int T, int TP2, int n, double in
 #pragma unroll
       for (int u = 0; u < kU; u++) mv[u] = (i0 + u * Q < n) ? load_min(t, i0 + u * Q) : inf;
 #pragma unroll
-      for (int u = 0; u < kU; u++) m = fmin(m, mv[u]);
+      for (int u = 0; u < kU; u++) m = mppi_min(m, mv[u]);
     }
   }
   smin[q * TP2 + t] = m;
   __syncthreads();
   m = smin[t];
-  for (int qq = 1; qq < Q; qq++) m = fmin(m, smin[qq * TP2 + t]);
+  for (int qq = 1; qq < Q; qq++) m = mppi_min(m, smin[qq * TP2 + t]);
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (t < T) {
     for (int i0 = q; i0 < n; i0 += kU * Q) {
@@ -360,8 +369,10 @@ __device__ __forceinline__ void mppi_apply_update(const A &a, double ul_cur, dou
   }
   else { a.u_next[t - 1] = nl; a.u_next[T + t - 1] = nr; }  // mppi.cpp:134
   if (t == T - 1) { a.u_next[T - 1] = a.uinit[0]; a.u_next[2 * T - 1] = a.uinit[1]; }   // mppi.cpp:136-137
-  a.stepstats[2 * t] = m;
-  a.stepstats[2 * t + 1] = sumw;
+  if (a.stepstats) {            // (min J, sum w) per step: only the weights tap reads them
+    a.stepstats[2 * t] = m;
+    a.stepstats[2 * t + 1] = sumw;
+  }
 }
 
 // ---- sharded rollouts: the exchange over NVLink peer memory ---------------------------------------------
@@ -455,15 +466,16 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
       const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
       c0[i] = __ldcg(c); c1[i] = __ldcg(c + 1); c2[i] = __ldcg(c + 2);
     }
-    m = fmin(m, c0[i].x);
+    m = mppi_min(m, c0[i].x);
   }
-  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) m = fmin(m, __ldcg(base + (size_t)p * p_stride));
-  m = warp_min(m);
+  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) m = mppi_min(m, __ldcg(base + (size_t)p * p_stride));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = mppi_min(m, __shfl_xor_sync(kFullMask, m, d));
   if (lane == 0) red[warp][0] = m;
   __syncthreads();
   m = red[0][0];
 #pragma unroll
-  for (int w = 1; w < NWARP; w++) m = fmin(m, red[w][0]);
+  for (int w = 1; w < NWARP; w++) m = mppi_min(m, red[w][0]);
   S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
@@ -483,7 +495,7 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
     DL += d2.x; DR += d2.y;
   }
   S = warp_sum(S); A = warp_sum(A); B = warp_sum(B); DL = warp_sum(DL); DR = warp_sum(DR);
-  __syncthreads();
+  // (columns 1..5: the minima in column 0 may still be read by slower warps)
   if (lane == 0) { red[warp][1] = S; red[warp][2] = A; red[warp][3] = B; red[warp][4] = DL; red[warp][5] = DR; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -529,10 +541,6 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
   double m, S, A, B, DL, DR;
   mppi_block_merge<NT, FASTEXP>(a.partials, a.n_roll, 6, 6 * a.n_roll, t, a.inv_lambda, m, S, A, B, DL, DR);
   mppi_stamp(a, 5);
-  if (threadIdx.x == 0) {
-    double *o = a.merged + (size_t)t * 6;
-    o[0] = m; o[1] = S; o[2] = A; o[3] = B; o[4] = DL; o[5] = DR;
-  }
   if (a.nranks > 1) mppi_exchange_step<NT, FASTEXP>(a, t, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
   mppi_apply_update(a, ul_cur, ur_cur, t, m, S, A, B, DL, DR);
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
       }
       double M = m0;
 #pragma unroll
-      for (int p = 0; p < kMppiBatch; p++) M = fmin(M, Jc[p]);
+      for (int p = 0; p < kMppiBatch; p++) M = Jc[p] < M ? Jc[p] : M;      // (no NaN among costs: a plain compare, not fmin's six instructions)
       // weight of a member = 2^((M - J) k2) through the SFU in binary32: the exponent difference is formed in fp64 (that is
       // where the conditioning sits), the weight itself needs the 1e-5 of the contract, not 1e-16.  A member that is not
       // there (J = +inf) gets 2^-inf = 0, weights below 2^-126 flush to zero: no branch anywhere.  (All absent: M = +inf
@@ -999,10 +1007,10 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
       const int tid_a = grp(i) + t % G, sa = t / G;
       v[0] = acc_base[sa * NT + tid_a];
       v[1] = (double)accf_base[(sa * 3) * NT + tid_a];
-      v[2] = (double)accf_base[(sa * 3 + 1) * NT + tid_a] * a.sigL;       // the sums were taken over the variates
-      v[3] = (double)accf_base[(sa * 3 + 2) * NT + tid_a] * a.sigR;
+      v[2] = (double)accf_base[(sa * 3 + 1) * NT + tid_a];                 // sums over the VARIATES: scaled by sigma once, after the merge
+      v[3] = (double)accf_base[(sa * 3 + 2) * NT + tid_a];
       const float2 z = reinterpret_cast<const float2 *>(dz4 + (sd / 2) * NT + tid_d)[sd & 1];
-      v[4] = (double)z.x * a.sigL; v[5] = (double)z.y * a.sigR;
+      v[4] = (double)z.x; v[5] = (double)z.y;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = acc_base[(sd * 4 + j) * NT + tid_d];
@@ -1011,6 +1019,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   };
   double v[6];
   mppi_merge_sets<NT, FAST>(T, TP2, NW * R, a.inv_lambda, scratch, cta_min, cta_set, v);
+  if (FAST) { v[2] *= a.sigL; v[3] *= a.sigR; v[4] *= a.sigL; v[5] *= a.sigR; }
   const int n_cta = a.n_roll;
   if (x < T) {
     double *o = a.partials + ((size_t)x * n_cta + blockIdx.x) * 6;
