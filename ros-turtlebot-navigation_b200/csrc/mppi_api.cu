@@ -45,6 +45,7 @@ struct b2n_mppi
   float4 *d_z[2] = {nullptr, nullptr};
   long long z_call[2] = {-1, -1};        // the call number whose variates a buffer holds (-1: none)
   uint64_t z_seed[2] = {0, 0};
+  int noise_ctas_per_sm = 8;             // B2N_MPPI_NOISE_CTAS: resident CTAs of the noise kernel per SM (it shares the SMs with a call's tail)
   bool noise_ahead = true;               // B2N_MPPI_NOISE_AHEAD=0: draw a call's variates in front of the call instead of behind the previous one
   double *d_merged = nullptr;            // [T][6]
   double *d_gathered = nullptr;          // [nranks][T][6]
@@ -276,7 +277,7 @@ int ensure_noise(b2n_mppi *h, uint32_t call, int slot, bool pdl)
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   const unsigned want = (unsigned)((n + 255) / 256);
-  cfg.gridDim = dim3(std::max(1u, std::min(want, (unsigned)h->n_sm * 8u))); cfg.blockDim = dim3(256); cfg.stream = h->stream;
+  cfg.gridDim = dim3(std::max(1u, std::min(want, (unsigned)h->n_sm * (unsigned)h->noise_ctas_per_sm))); cfg.blockDim = dim3(256); cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -466,6 +467,7 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
   B2N_TRY(cudaHostGetDevicePointer(&h->d_out_host, h->h_out, 0));
   if (const char *env = std::getenv("B2N_MPPI_PDL")) h->use_pdl = env[0] != '0';
   if (const char *env = std::getenv("B2N_MPPI_NOISE_AHEAD")) h->noise_ahead = env[0] != '0';
+  if (const char *env = std::getenv("B2N_MPPI_NOISE_CTAS")) { const int n = std::atoi(env); if (n >= 1 && n <= 8) h->noise_ctas_per_sm = n; }
   B2N_TRY(cudaStreamSynchronize(h->stream));
 #undef B2N_TRY
   *out = h;

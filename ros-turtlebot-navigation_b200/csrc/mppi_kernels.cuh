@@ -666,6 +666,14 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   // launched programmatically dependent on the previous call: everything above overlapped its tail; the plan it writes
   // is read from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the variates of the first pass: in flight while this CTA waits for the plan (the grid in front - the noise kernel - is
+  // complete from here on)
+  float4 zn[FAST ? S / 2 : 1];
+  if (z_ahead && base < a.K) {
+    const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
+#pragma unroll
+    for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
+  }
   // the grid in front of this one may be the kernel that drew this call's variates: the call before THAT one counts its
   // finished plan steps (normally long there)
   if (a.plan_need && threadIdx.x == 0) {
@@ -750,12 +758,6 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     }
     __syncwarp();
   };
-  float4 zn[FAST ? S / 2 : 1];
-  if (z_ahead && base < a.K) {
-    const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
-#pragma unroll
-    for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
-  }
   int buf = 0;
   bool have_noise = true;
   for (; base < a.K; base += nw * R, buf ^= (NBUF - 1)) {
