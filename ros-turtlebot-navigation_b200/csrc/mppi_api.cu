@@ -37,7 +37,10 @@ struct b2n_mppi
   float *d_states = nullptr;             // [ring][K][T][3]
   int ring = 1, ring_pos = 0, last_slot = 0;
   double *d_partials = nullptr;          // [T][grid][6]
-  unsigned long long *d_sync = nullptr;  // [2] fused calls: rollout CTAs counted in, plan steps completed (both monotonic)
+  MppiLL *d_ll_partials = nullptr;       // [T][3][grid] tagged words: the fused call's CTA partials (MppiArgs::ll_partials)
+  MppiLL *d_ll_plan[2] = {nullptr, nullptr};  // [T] tagged words: the plan a fused call leaves for the next one's CTAs
+  unsigned long long *d_arrive = nullptr;     // warps of rollout CTAs that have sent their partial words (a hint for the merger CTAs)
+  uint32_t plan_tag = 0;                 // tag of the fused call that wrote the current plan; 0: written some other way (plain array, stream order)
   unsigned long long fused_calls = 0;    // fused calls enqueued so far
   unsigned long long *d_dbg = nullptr;   // [grid][8] stage timestamps, B2N_MPPI_DEBUG_TIMES=1 (tuning runs)
   int last_fast = 0;                     // the last call ran the FAST instantiation
@@ -237,10 +240,14 @@ void arm_tail(b2n_mppi *h, MppiArgs &a)
 {
   const b2n_mppi_params &p = h->p;
   a.tail = 1;
-  a.plan_need = (unsigned long long)h->T * h->fused_calls;      // every step of every earlier fused call
   h->fused_calls++;
-  a.arrive = h->d_sync; a.arrive_need = (unsigned long long)h->grid * h->fused_calls;
-  a.plan_seq = h->d_sync + 1;
+  a.tag = (uint32_t)(h->fused_calls % 0xFFFFFFFFull) + 1u;      // never 0, distinct from the tags a buffer can still hold
+  a.plan_tag = h->plan_tag;
+  a.ll_partials = h->d_ll_partials;
+  a.arrive = h->d_arrive; a.arrive_need = (unsigned long long)h->grid * (unsigned long long)((h->T + 31) / 32) * h->fused_calls;
+  a.ll_plan = h->d_ll_plan[(h->fused_calls & 1ull) ^ 1ull];     // fused call n writes buffer n & 1: its predecessor wrote the other one
+  a.ll_plan_next = h->d_ll_plan[h->fused_calls & 1ull];
+  h->plan_tag = a.tag;
   a.k_total = (double)(p.rollouts_total > 0 ? p.rollouts_total : p.rollouts);
   a.umax = p.max_wheel_vel;
   a.uinit[0] = h->uinit[0]; a.uinit[1] = h->uinit[1];
@@ -367,6 +374,7 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behin
     B2N_REQUIRE(r == ncclSuccess, B2N_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(r));
     u.partials = h->d_gathered; u.n_partials = h->nranks; u.p_stride = 6 * h->T; u.t_stride = 6; u.merge_only = 0;
     if (int rc = launch_update(h, u)) return rc;
+    h->plan_tag = 0;    // written by the update kernel: the plain array, ordered by the stream
   }
 
   h->cur ^= 1;
@@ -452,8 +460,14 @@ int b2n_mppi_create(const b2n_mppi_params *params, b2n_mppi **out)
     B2N_TRY(cudaMalloc(&h->d_z[0], KT / 2 * sizeof(float4)));
     B2N_TRY(cudaMalloc(&h->d_z[1], KT / 2 * sizeof(float4)));
   }
-  B2N_TRY(cudaMalloc(&h->d_sync, 2 * sizeof(unsigned long long)));
-  B2N_TRY(cudaMemsetAsync(h->d_sync, 0, 2 * sizeof(unsigned long long), h->stream));
+  B2N_TRY(cudaMalloc(&h->d_ll_partials, (size_t)h->grid * T * 3 * sizeof(MppiLL)));
+  B2N_TRY(cudaMemsetAsync(h->d_ll_partials, 0, (size_t)h->grid * T * 3 * sizeof(MppiLL), h->stream));     // tag 0: no call's
+  B2N_TRY(cudaMalloc(&h->d_arrive, sizeof(unsigned long long)));
+  B2N_TRY(cudaMemsetAsync(h->d_arrive, 0, sizeof(unsigned long long), h->stream));
+  for (int i = 0; i < 2; i++) {
+    B2N_TRY(cudaMalloc(&h->d_ll_plan[i], (size_t)T * sizeof(MppiLL)));
+    B2N_TRY(cudaMemsetAsync(h->d_ll_plan[i], 0, (size_t)T * sizeof(MppiLL), h->stream));
+  }
   if (const char *env = std::getenv("B2N_MPPI_DEBUG_TIMES")) {
     if (env[0] == '1') {
       B2N_TRY(cudaMalloc(&h->d_dbg, (size_t)(h->grid + T) * kMppiDbgSlots * sizeof(unsigned long long)));
@@ -485,7 +499,7 @@ void b2n_mppi_destroy(b2n_mppi *h)
   cudaFree(h->xchg);
   for (auto e : h->ev) cudaEventDestroy(e);
   cudaFree(h->d_u[0]); cudaFree(h->d_u[1]); cudaFree(h->d_states); cudaFree(h->d_partials);
-  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_stepstats); cudaFree(h->d_sync); cudaFree(h->d_dbg);
+  cudaFree(h->d_merged); cudaFree(h->d_gathered); cudaFree(h->d_stepstats); cudaFree(h->d_ll_partials); cudaFree(h->d_arrive); cudaFree(h->d_ll_plan[0]); cudaFree(h->d_ll_plan[1]); cudaFree(h->d_dbg);
   cudaFree(h->d_z[0]); cudaFree(h->d_z[1]);
   cudaFree(h->d_ext); cudaFree(h->d_J); cudaFree(h->d_du); cudaFree(h->d_w); cudaFree(h->d_obs);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -506,6 +520,7 @@ int b2n_mppi_set_initial_controls(b2n_mppi *h, double ul, double ur)
   for (int t = 0; t < h->T; t++) { u[t] = ul; u[h->T + t] = ur; }
   B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));
+  h->plan_tag = 0;      // the plain array is the plan now
   return B2N_OK;
 }
 
@@ -662,6 +677,7 @@ int b2n_mppi_set_plan(b2n_mppi *h, const double *u, size_t count)
   for (size_t i = 0; i < count; i++) h->plan_abs_max = std::max(h->plan_abs_max, std::fabs(u[i]));
   B2N_CUDA(cudaMemcpyAsync(h->d_u[h->cur], u, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   B2N_CUDA(cudaStreamSynchronize(h->stream));
+  h->plan_tag = 0;      // the plain array is the plan now
   return B2N_OK;
 }
 
@@ -826,7 +842,7 @@ int b2n_mppi_time_rollout(b2n_mppi *h, double x, double y, double theta, int lau
     if (int rc = ensure_noise(h, h->call, (int)(h->call & 1u), false)) return rc;
     a.zbuf = h->d_z[h->call & 1u];
   }
-  a.plan_seq = h->d_sync + 1; a.plan_need = (unsigned long long)h->T * h->fused_calls;
+  a.plan_tag = h->plan_tag; a.ll_plan = h->d_ll_plan[h->fused_calls & 1ull];      // the plan as the last fused call left it
   cudaEvent_t e0, e1;
   B2N_CUDA(cudaEventCreate(&e0));
   B2N_CUDA(cudaEventCreate(&e1));

@@ -42,6 +42,8 @@ constexpr int kMppiMaxT = 256;               // 32 lanes x 8 steps
 constexpr int kMppiMaxRanks = 64;
 constexpr int kMppiXchgWords = 12;           // 6 doubles = 12 payload halves
 
+struct MppiLL;
+
 struct MppiArgs
 {
   // model, cost, sampling
@@ -75,8 +77,19 @@ struct MppiArgs
   // ---- fused tail: merge tree, exchange, update (mppi.cpp:112-137) ----
   int tail;                // 0: stop after the CTA partials (NCCL transport, bench hook b2n_mppi_time_rollout)
   int n_roll;              // rollout CTAs (block indices below this); with tail: gridDim.x = n_roll + T, the rest are mergers
-  unsigned long long *arrive;        // rollout CTAs that have published their partial, all fused calls of the handle together
-  unsigned long long arrive_need;    //   its value when this call's are all in: n_roll x (number of fused calls so far)
+  // hand-over inside the fused call and from call to call WITHOUT fences or counters: doubles travel in pairs as 32-byte
+  // words of four 8-byte units (4 bytes of payload, the call's tag).  8-byte units are single transactions, so a unit that
+  // shows the tag IS its payload; the reader spins on the words it needs and nothing else is ordered (the LL protocol of
+  // NCCL, on L2)
+  MppiLL *ll_partials;     // [T][3][n_roll] this call's CTA partials, tagged `tag`: merger CTA t reads step t's
+  const MppiLL *ll_plan;   // [T] the current plan (uL_t, uR_t) as tagged words, valid when plan_tag != 0 (the call before was a fused one)
+  MppiLL *ll_plan_next;    // [T] the plan this call writes, tagged `tag`
+  uint32_t tag, plan_tag;  // never 0
+  // a hint, not a synchronisation: warps that have sent their partial words count themselves in with a relaxed reduction
+  // (nothing waits for it), and a merger CTA watches this one word instead of spinning on n_roll x 96 bytes; the words
+  // themselves are still checked by their tags when they are read
+  unsigned long long *arrive;        // monotonic over the handle's fused calls
+  unsigned long long arrive_need;    // its value when this call's are all in: n_roll x ceil(T / 32) per fused call
   double k_total, umax;
   double uinit[2];
   double *u_next;          // [2][T]
@@ -86,8 +99,6 @@ struct MppiArgs
   double *stepstats;       // [T][2] (min J, sum w) for the weights tap
   double *merged;          // [T][6] this rank's merged sums (tap)
   unsigned long long *dbg;       // [grid][8] stage timestamps (globaltimer ns) of every CTA's thread 0, tuning runs only (null: off)
-  unsigned long long *plan_seq;  // steps whose update is complete, all fused calls of the handle together (device memory):
-  unsigned long long plan_need;  //   the value the CTAs of this call wait for before they read the plan (T per earlier call)
   // sharded job: peer-memory exchange areas [2 parities][nranks][T][12 words], see mppi_exchange()
   int rank, nranks, parity;
   uint32_t call_id;
@@ -112,6 +123,32 @@ struct MppiUpdateArgs
 
 // minimum of two costs (never NaN): a compare and a select, where fmin spends half a dozen instructions on NaN rules
 __device__ __forceinline__ double mppi_min(double a, double b) { return b < a ? b : a; }
+
+// tagged 32-byte words (see MppiArgs::ll_partials): two doubles, each 4-byte half next to the tag in its own 8-byte unit.
+// One 256-bit store writes a whole 32-byte sector (a narrower store would leave a partially valid sector in L2, and the
+// reader's load would then wait for the rest of it from DRAM)
+struct __align__(32) MppiLL { unsigned long long w[4]; };
+
+__device__ __forceinline__ void mppi_ll_store(MppiLL *dst, double v0, double v1, uint32_t tag)
+{
+  const unsigned long long tg = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.gpu.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(tg | (uint32_t)__double2loint(v0)),
+               "l"(tg | (uint32_t)__double2hiint(v0)), "l"(tg | (uint32_t)__double2loint(v1)), "l"(tg | (uint32_t)__double2hiint(v1)) : "memory");
+}
+__device__ __forceinline__ bool mppi_ll_load(const MppiLL *src, uint32_t tag, double &v0, double &v1)
+{
+  unsigned long long a, b, c, d;
+  asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src) : "memory");
+  v0 = __hiloint2double((int)(uint32_t)b, (int)(uint32_t)a);
+  v1 = __hiloint2double((int)(uint32_t)d, (int)(uint32_t)c);
+  return ((uint32_t)(a >> 32) == tag) & ((uint32_t)(b >> 32) == tag) & ((uint32_t)(c >> 32) == tag) & ((uint32_t)(d >> 32) == tag);
+}
+__device__ __forceinline__ void mppi_ll_wait(const MppiLL *src, uint32_t tag, double &v0, double &v1)
+{
+  unsigned spins = 0;
+  while (!mppi_ll_load(src, tag, v0, v1))
+    if (++spins == (1u << 27)) __trap();            // about a minute without the word: fail loudly, not silently
+}
 
 constexpr int kMppiObsTile = 32;             // cells per side of the obstacle-field tile staged through TMA
 
@@ -272,7 +309,7 @@ __device__ __forceinline__ void mppi_stamp(const MppiArgs &a, int j)
 {
   if (a.dbg && threadIdx.x == 0) {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");      // (the clobber keeps it on its side of a barrier)
     a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + j] = t;
   }
 }
@@ -342,7 +379,7 @@ __device__ __forceinline__ void mppi_merge_sets(int T, int TP2, int n, double in
 
 // the control update of mppi.cpp:112-137 for step t from the fully merged sums (one thread)
 template <class A>
-__device__ __forceinline__ void mppi_apply_update(const A &a, double ul_cur, double ur_cur, int t, double m, double S, double Aw, double Bw, double DL, double DR)
+__device__ __forceinline__ double2 mppi_apply_update(const A &a, double ul_cur, double ur_cur, int t, double m, double S, double Aw, double Bw, double DL, double DR)
 {
   const int T = a.T;
   // w_k = exp(-(J_k - min)/lambda) + 1e-8, normalised (mppi.cpp:117-118)
@@ -373,6 +410,7 @@ __device__ __forceinline__ void mppi_apply_update(const A &a, double ul_cur, dou
     a.stepstats[2 * t] = m;
     a.stepstats[2 * t + 1] = sumw;
   }
+  return make_double2(nl, nr);
 }
 
 // ---- sharded rollouts: the exchange over NVLink peer memory ---------------------------------------------
@@ -421,6 +459,7 @@ __device__ __forceinline__ void mppi_exchange_step(const MppiArgs &a, int t, dou
     all[r][w] = (uint32_t)got;
   }
   __syncthreads();
+  mppi_stamp(a, 7);
   // fold the nranks results in rank order (identical on every rank).  The rescale factors are independent of one
   // another: thread r computes rank r's (one exponential each, side by side), thread 0 then runs the ordered sums
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -446,9 +485,12 @@ __device__ __forceinline__ void mppi_exchange_step(const MppiArgs &a, int t, dou
 // merge of one step's partials by one CTA of NT threads: minimum first, then every partial rescaled once (independent
 // exponentials), plain sums in a fixed order.  partial p of step t at partials + p * p_stride + t * t_stride (doubles).
 // The result is valid in thread 0.
-template <int NT, bool FASTEXP>
+// LL: the partials are the tagged words of MppiArgs::ll_partials ([T][6][n]); every thread spins on its own until they show
+// the call's tag - the wait for the rollout CTAs and the load are one and the same L2 round trip.
+template <int NT, bool FASTEXP, bool LL = false>
 __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_partials, int p_stride, int t_stride, int t, double inv_lambda, double &m,
-                                                 double &S, double &A, double &B, double &DL, double &DR)
+                                                 double &S, double &A, double &B, double &DL, double &DR, const MppiLL *ll = nullptr, uint32_t tag = 0,
+                                                 unsigned long long *stamp = nullptr)
 {
   constexpr int kPer = 2;                                   // partials held in registers per thread (one L2 round trip)
   constexpr int NWARP = NT / 32;
@@ -462,13 +504,39 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
   for (int i = 0; i < kPer; i++) {
     const int p = threadIdx.x + i * NT;
     c0[i] = make_double2(inf, 0.0); c1[i] = make_double2(0.0, 0.0); c2[i] = make_double2(0.0, 0.0);
-    if (p < n_partials) {
+    if (!LL && p < n_partials) {
       const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
       c0[i] = __ldcg(c); c1[i] = __ldcg(c + 1); c2[i] = __ldcg(c + 2);
     }
-    m = mppi_min(m, c0[i].x);
   }
-  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) m = mppi_min(m, __ldcg(base + (size_t)p * p_stride));
+  const MppiLL *lbase = ll + (size_t)t * 3 * n_partials;    // word j of partial p at lbase[j * n + p]: a warp's loads are contiguous
+  if (LL) {
+    // all words of the thread's partials in flight together, again until every one of them shows the tag
+    unsigned spins = 0;
+    for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < kPer; i++) {
+        const int p = threadIdx.x + i * NT;
+        if (p < n_partials) {
+          const MppiLL *w = lbase + p;
+          ok &= mppi_ll_load(w, tag, c0[i].x, c0[i].y);
+          ok &= mppi_ll_load(w + n_partials, tag, c1[i].x, c1[i].y);
+          ok &= mppi_ll_load(w + 2 * (size_t)n_partials, tag, c2[i].x, c2[i].y);
+        }
+      }
+      if (ok) break;
+      if (++spins == (1u << 27)) __trap();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPer; i++) m = mppi_min(m, c0[i].x);
+  for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) {
+    double v0, v1;
+    if (LL) mppi_ll_wait(lbase + p, tag, v0, v1);
+    else v0 = __ldcg(base + (size_t)p * p_stride);
+    m = mppi_min(m, v0);
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = mppi_min(m, __shfl_xor_sync(kFullMask, m, d));
   if (lane == 0) red[warp][0] = m;
@@ -476,6 +544,11 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
   m = red[0][0];
 #pragma unroll
   for (int w = 1; w < NWARP; w++) m = mppi_min(m, red[w][0]);
+  if (stamp && threadIdx.x == 0) {            // tuning runs: every thread's partials are in
+    unsigned long long now;       // (the operand ties the read to data from behind the barrier: BAR.SYNC.DEFER_BLOCKING lets a warp run on)
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "d"(m) : "memory");
+    *stamp = now;
+  }
   S = 0.0; A = 0.0; B = 0.0; DL = 0.0; DR = 0.0;
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
@@ -486,8 +559,16 @@ __device__ __forceinline__ void mppi_block_merge(const double *partials, int n_p
     DL += c2[i].x; DR += c2[i].y;
   }
   for (int p = threadIdx.x + kPer * NT; p < n_partials; p += NT) {
-    const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
-    const double2 d0 = __ldcg(c), d1 = __ldcg(c + 1), d2 = __ldcg(c + 2);
+    double2 d0, d1, d2;
+    if (LL) {
+      const MppiLL *w = lbase + p;
+      mppi_ll_wait(w, tag, d0.x, d0.y);
+      mppi_ll_wait(w + n_partials, tag, d1.x, d1.y);
+      mppi_ll_wait(w + 2 * (size_t)n_partials, tag, d2.x, d2.y);
+    } else {
+      const double2 *c = reinterpret_cast<const double2 *>(base + (size_t)p * p_stride);
+      d0 = __ldcg(c); d1 = __ldcg(c + 1); d2 = __ldcg(c + 2);
+    }
     if (d0.x != inf) {
       const double f = (d0.x == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - d0.x) * inv_lambda);
       S = fma(d0.y, f, S); A = fma(d1.x, f, A); B = fma(d1.y, f, B);
@@ -514,38 +595,34 @@ __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
   // (a merger can be resident before the previous call has finished: the plan's step count first, as the rollout CTAs do)
   double ul_cur = 0.0, ur_cur = 0.0;
   if (threadIdx.x == 0) {
-    if (a.plan_need) {
-      unsigned long long seen;
-      unsigned spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.plan_seq) : "memory");
-        if (++spins == (1u << 28)) __trap();
-      } while (seen < a.plan_need);
-    }
-    ul_cur = a.u_plan[t]; ur_cur = a.u_plan[a.T + t];
+    if (a.plan_tag) mppi_ll_wait(a.ll_plan + t, a.plan_tag, ul_cur, ur_cur);
+    else { ul_cur = a.u_plan[t]; ur_cur = a.u_plan[a.T + t]; }
   }
   // the next grid in the stream (the kernel that draws the next call's variates) may take the SMs the rollout CTAs leave
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // every rollout CTA of this call has published its partial (a monotonic count over the handle's fused calls)
+  mppi_stamp(a, 4);
   if (threadIdx.x == 0) {
     unsigned long long seen;
     unsigned spins = 0;
     for (;;) {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.arrive) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.arrive) : "memory");
       if (seen >= a.arrive_need) break;
       if (++spins == (1u << 28)) __trap();
     }
   }
   __syncthreads();
-  mppi_stamp(a, 4);
+  // every rollout CTA's partial of this step (sent, by the count; each word is checked by its tag)
   double m, S, A, B, DL, DR;
-  mppi_block_merge<NT, FASTEXP>(a.partials, a.n_roll, 6, 6 * a.n_roll, t, a.inv_lambda, m, S, A, B, DL, DR);
+  mppi_block_merge<NT, FASTEXP, true>(nullptr, a.n_roll, 0, 0, t, a.inv_lambda, m, S, A, B, DL, DR, a.ll_partials, a.tag,
+                                      a.dbg ? a.dbg + (size_t)blockIdx.x * kMppiDbgSlots + 3 : nullptr);
   mppi_stamp(a, 5);
   if (a.nranks > 1) mppi_exchange_step<NT, FASTEXP>(a, t, m, S, A, B, DL, DR);
   if (threadIdx.x != 0) return;
-  mppi_apply_update(a, ul_cur, ur_cur, t, m, S, A, B, DL, DR);
-  // this step of the plan is complete: the next call's CTAs wait for all T
-  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.plan_seq), "l"(1ull) : "memory");
+  const double2 u = mppi_apply_update(a, ul_cur, ur_cur, t, m, S, A, B, DL, DR);
+  // this step of the plan for the next call's CTAs (one slot to the left, as u_next): tagged words, nothing to order
+  const int T = a.T;
+  if (t > 0) mppi_ll_store(a.ll_plan_next + t - 1, u.x, u.y, a.tag);
+  if (t == T - 1) mppi_ll_store(a.ll_plan_next + T - 1, a.uinit[0], a.uinit[1], a.tag);
   mppi_stamp(a, 6);
 }
 
@@ -674,17 +751,6 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
 #pragma unroll
     for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
   }
-  // the grid in front of this one may be the kernel that drew this call's variates: the call before THAT one counts its
-  // finished plan steps (normally long there)
-  if (a.plan_need && threadIdx.x == 0) {
-    unsigned long long seen;
-    unsigned spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.plan_seq) : "memory");
-      if (++spins == (1u << 28)) __trap();
-    } while (seen < a.plan_need);
-  }
-  __syncthreads();
   // the obstacle-field tile around the start pose (occupancy-grid tiles staged through TMA, north_star): rows of the tile
   // are contiguous in the field, one bulk copy each, all completing on one mbarrier.  After the wait: the field may have
   // been written by the kernel that precedes this one in the stream (b2n_pf_write_distance_field)
@@ -695,9 +761,16 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
     for (int i = 0; i < kMppiObsTile; i++)
       tma_load_1d(tile + i * kMppiObsTile, a.obs_dist + (size_t)(a.obs_ti0 + i) * a.obs_ysize + a.obs_tj0, kMppiObsTile * sizeof(float), tile_bar);
   }
-  for (int i = threadIdx.x; i < 2 * TP; i += NT) {
-    const int row = i / TP, t = i - row * TP;
-    plan[i] = t < T ? a.u_plan[row * T + t] : 0.0;        // plain (coherent) loads: the previous call's tail wrote this buffer
+  // the plan.  Behind a fused call: its tagged words, each thread spinning on its own until the merger CTA of that step has
+  // written it (the grid in front of this one may be the noise kernel; the call in front of THAT is normally long done).
+  // Otherwise the plain array, ordered by the stream
+  for (int t = threadIdx.x; t < TP; t += NT) {
+    double ul = 0.0, ur = 0.0;
+    if (t < T) {
+      if (a.plan_tag) mppi_ll_wait(a.ll_plan + t, a.plan_tag, ul, ur);
+      else { ul = a.u_plan[t]; ur = a.u_plan[T + t]; }
+    }
+    plan[t] = ul; plan[TP + t] = ur;
   }
   __syncthreads();
   if (obs_on && a.obs_ti0 >= 0) mbar_wait(tile_bar, 0);
@@ -1023,19 +1096,33 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   mppi_merge_sets<NT, FAST>(T, TP2, NW * R, a.inv_lambda, scratch, cta_min, cta_set, v);
   if (FAST) { v[2] *= a.sigL; v[3] *= a.sigR; v[4] *= a.sigL; v[5] *= a.sigR; }
   const int n_cta = a.n_roll;
+  if (a.dbg && x == 0) {          // tuning runs: the CTA's sets are merged (tied to the result)
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "d"(v[1]) : "memory");
+    a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + 3] = now;
+  }
   if (x < T) {
+    if (a.tail) {
+      // to merger CTA x, which spins on these words: no count, no fence
+      MppiLL *w = a.ll_partials + (size_t)x * 3 * n_cta + blockIdx.x;
+#pragma unroll
+      for (int j = 0; j < 3; j++) mppi_ll_store(w + (size_t)j * n_cta, v[2 * j], v[2 * j + 1], a.tag);
+      if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(a.arrive), "l"(1ull) : "memory");
+    }
+    // the plain copy: the update kernel of the NCCL transport and the partials tap read it after the grid
     double *o = a.partials + ((size_t)x * n_cta + blockIdx.x) * 6;
     reinterpret_cast<double2 *>(o)[0] = make_double2(v[0], v[1]);
     reinterpret_cast<double2 *>(o)[1] = make_double2(v[2], v[3]);
     reinterpret_cast<double2 *>(o)[2] = make_double2(v[4], v[5]);
   }
   mppi_stamp(a, 2);
-  if (!a.tail) return;
-  // count this CTA in: a release reduction by one thread after the barrier covers every thread's stores, and there is
-  // nothing to wait for - the merger CTAs watch the count
-  __syncthreads();
-  if (x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.arrive), "l"(1ull) : "memory");
-  mppi_stamp(a, 3);
+  if (a.dbg && a.tail && x == 0) {          // tuning runs: when this thread's last word has landed in L2 and come back
+    double r0, r1;
+    mppi_ll_wait(a.ll_partials + 2 * (size_t)n_cta + blockIdx.x, a.tag, r0, r1);
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "d"(r0) : "memory");
+    a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + 7] = now;
+  }
 }
 
 // ---- the variates of the NEXT call, drawn ahead ------------------------------------------------------------------------

@@ -19,7 +19,7 @@ m.setStateRing(16)
 m.seed(42)
 m.setWaypoint(pkg.Pose(theta=1.5707, x=1.0, y=0.0))
 pose = pkg.Pose(theta=0.0, x=0.0, y=0.0)
-names = ["loop start", "loop end", "partial written", "counted in", "merger: all in", "merger: merged", "merger: updated", "-"]
+names = ["loop start", "loop end", "partial written", "merger: partials in", "merger: resident", "merger: merged", "merger: updated", "-"]
 for rep in range(6):
     for _ in range(10):
         m.newControls(pose)
@@ -33,11 +33,11 @@ for rep in range(6):
         if len(col):
             print("  %-16s n=%4d  min %7.2f  median %7.2f  max %7.2f us" % (n, len(col), col.min() / 1e3, np.median(col) / 1e3, col.max() / 1e3))
     # per-CTA stage durations
-    for j in (1, 2, 3, 5, 6):
-        ok = (d[:, j] >= t0) & (d[:, j - 1] >= t0)
+    for i, j in ((0, 1), (1, 2), (4, 3), (3, 5), (5, 6)):
+        ok = (d[:, j] >= t0) & (d[:, i] >= t0)
         if ok.any():
-            dd = (d[ok, j] - d[ok, j - 1]) / 1e3
-            print("  %-16s -> %-16s n=%4d  min %6.2f median %6.2f max %6.2f us" % (names[j - 1], names[j], ok.sum(), dd.min(), np.median(dd), dd.max()))
+            dd = (d[ok, j] - d[ok, i]) / 1e3
+            print("  %-16s -> %-16s n=%4d  min %6.2f median %6.2f max %6.2f us" % (names[i], names[j], ok.sum(), dd.min(), np.median(dd), dd.max()))
     ph = ["z load", "D sums", "(decl)", "local integration", "rot scan", "pos scan", "stage wait", "loss + stores", "cost scan", "softmax", "bulk store"]
     c = d[:-m.steps, 8:19]
     dc = np.diff(c, axis=1)
