@@ -88,6 +88,12 @@ struct MppiArgs
   // a hint, not a synchronisation: warps that have sent their partial words count themselves in with a relaxed reduction
   // (nothing waits for it), and a merger CTA watches this one word instead of spinning on n_roll x 96 bytes; the words
   // themselves are still checked by their tags when they are read
+  // pipelined calls: the next call does not wait for this grid (and everything in front of it) to COMPLETE.  What it reads
+  // from earlier grids it waits for by itself: the plan through its tagged words, the variates through the count of noise-
+  // kernel CTAs that have finished (a release reduction each; monotonic over the handle's noise launches)
+  int skip_wait;                     // 1: no griddepcontrol.wait (fused call behind a fused call, no device-resident input besides these two)
+  const unsigned long long *z_ready;
+  unsigned long long z_need;
   unsigned long long *arrive;        // monotonic over the handle's fused calls
   unsigned long long arrive_need;    // its value when this call's are all in: n_roll x ceil(T / 32) per fused call
   double k_total, umax;
@@ -310,7 +316,10 @@ __device__ __forceinline__ void mppi_stamp(const MppiArgs &a, int j)
   if (a.dbg && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");      // (the clobber keeps it on its side of a barrier)
-    a.dbg[(size_t)blockIdx.x * kMppiDbgSlots + j] = t;
+    unsigned long long *row = a.dbg + (size_t)blockIdx.x * kMppiDbgSlots;
+    if (j == 0) row[11] = row[0];           // the previous call's loop start / update: the period of pipelined calls
+    if (j == 6) row[12] = row[6];
+    row[j] = t;
   }
 }
 
@@ -414,72 +423,72 @@ __device__ __forceinline__ double2 mppi_apply_update(const A &a, double ul_cur, 
 }
 
 // ---- sharded rollouts: the exchange over NVLink peer memory ---------------------------------------------
-// Every rank owns an exchange area [2 call parities][nranks][T][12] of 8-byte words; peer[j] is rank j's area mapped
-// into this process (CUDA IPC).  Merger CTA t sends this rank's merged sums of step t to every rank (its own included:
-// one code path) in the low-latency style of NCCL's LL protocol: each 8-byte word carries 4 bytes of payload and the
-// 32-bit call id, and 8-byte stores are single NVLink transactions, so a word whose upper half shows the current call id
-// IS its payload - no fence, no separate flag, one NVLink write latency.  The CTA then spins on the 12 x nranks words of
-// its own area, and thread 0 folds the nranks results in rank order (identical on every rank, so the plan stays replicated
-// without a broadcast).  No NCCL call, no extra launch.
+// Every rank owns an exchange area [2 call parities][nranks][T][3] of tagged 32-byte words (MppiLL); peer[j] is rank j's
+// area mapped into this process (CUDA IPC).  Merger CTA t sends this rank's merged sums of step t to every rank (its own
+// included: one code path) in the low-latency style of NCCL's LL protocol: each 8-byte unit carries 4 bytes of payload
+// and the 32-bit call id, and 8-byte units are single NVLink transactions, so a unit whose upper half shows the current
+// call id IS its payload - no fence, no separate flag, one NVLink write latency.  Lane r of the CTA's first warp then spins
+// on rank r's three words in this rank's own area and the warp folds the nranks results with shuffles - a fixed tree, the
+// same on every rank, so the plan stays replicated bit for bit without a broadcast.  No NCCL call, no extra launch.
 // A slot of parity p is rewritten at call c + 2 only after its owner finished call c + 1, which needed this rank's
 // data of call c + 1, which was sent after this rank finished reading call c: two parities are enough.
+__device__ __forceinline__ void mppi_ll_store_sys(MppiLL *dst, double v0, double v1, uint32_t tag)
+{
+  const unsigned long long tg = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.sys.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(tg | (uint32_t)__double2loint(v0)),
+               "l"(tg | (uint32_t)__double2hiint(v0)), "l"(tg | (uint32_t)__double2loint(v1)), "l"(tg | (uint32_t)__double2hiint(v1)) : "memory");
+}
+__device__ __forceinline__ bool mppi_ll_load_sys(const MppiLL *src, uint32_t tag, double &v0, double &v1)
+{
+  unsigned long long a, b, c, d;
+  asm volatile("ld.relaxed.sys.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src) : "memory");
+  v0 = __hiloint2double((int)(uint32_t)b, (int)(uint32_t)a);
+  v1 = __hiloint2double((int)(uint32_t)d, (int)(uint32_t)c);
+  return ((uint32_t)(a >> 32) == tag) & ((uint32_t)(b >> 32) == tag) & ((uint32_t)(c >> 32) == tag) & ((uint32_t)(d >> 32) == tag);
+}
+
 template <int NT, bool FASTEXP>
 __device__ __forceinline__ void mppi_exchange_step(const MppiArgs &a, int t, double &m, double &S, double &A, double &B, double &DL, double &DR)
 {
-  __shared__ uint32_t mine[kMppiXchgWords];
-  __shared__ uint32_t all[kMppiMaxRanks][kMppiXchgWords];
-  __shared__ double fac[kMppiMaxRanks];
-  const int T = a.T, par = a.parity;
-  if (threadIdx.x == 0) {
-    const double v[6] = {m, S, A, B, DL, DR};
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      mine[2 * i] = (uint32_t)__double2loint(v[i]);
-      mine[2 * i + 1] = (uint32_t)__double2hiint(v[i]);
-    }
-  }
+  __shared__ double mine[6];
+  const int T = a.T, par = a.parity, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mine[0] = m; mine[1] = S; mine[2] = A; mine[3] = B; mine[4] = DL; mine[5] = DR; }
   __syncthreads();
-  const int n_words = a.nranks * kMppiXchgWords;
-  for (int i = threadIdx.x; i < n_words; i += NT) {
-    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
-    // word w of this rank's slot in rank r's area
-    unsigned long long *dst = a.peer[r] + (((size_t)par * a.nranks + a.rank) * T + t) * kMppiXchgWords + w;
-    const unsigned long long packed = ((unsigned long long)a.call_id << 32) | mine[w];
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(packed) : "memory");
+  for (int i = threadIdx.x; i < 3 * a.nranks; i += NT) {
+    const int r = i / 3, j = i - 3 * r;
+    // word j of this rank's slot in rank r's area
+    MppiLL *dst = reinterpret_cast<MppiLL *>(a.peer[r]) + (((size_t)par * a.nranks + a.rank) * T + t) * 3 + j;
+    mppi_ll_store_sys(dst, mine[2 * j], mine[2 * j + 1], a.call_id);
   }
-  for (int i = threadIdx.x; i < n_words; i += NT) {
-    const int r = i / kMppiXchgWords, w = i % kMppiXchgWords;
-    const unsigned long long *src = a.peer[a.rank] + (((size_t)par * a.nranks + r) * T + t) * kMppiXchgWords + w;
-    unsigned long long got;
-    unsigned polls = 0;
-    do {
-      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
-      if (++polls == (1u << 27)) __trap();          // about a minute without the peer's word: fail loudly, not silently
-    } while ((uint32_t)(got >> 32) != a.call_id);
-    all[r][w] = (uint32_t)got;
-  }
-  __syncthreads();
-  mppi_stamp(a, 7);
-  // fold the nranks results in rank order (identical on every rank).  The rescale factors are independent of one
-  // another: thread r computes rank r's (one exponential each, side by side), thread 0 then runs the ordered sums
+  if (threadIdx.x >= 32) return;
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
-  auto val = [&](int r, int i) { return __hiloint2double((int)all[r][2 * i + 1], (int)all[r][2 * i]); };
-  m = inf;
-  for (int r = 0; r < a.nranks; r++) m = fmin(m, val(r, 0));
-  if ((int)threadIdx.x < a.nranks) {
-    const double mr = val((int)threadIdx.x, 0);
-    fac[threadIdx.x] = (mr == inf) ? 0.0 : (mr == m) ? 1.0 : mppi_exp_neg<FASTEXP>((m - mr) * a.inv_lambda);
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  S = A = B = DL = DR = 0.0;
-  for (int r = 0; r < a.nranks; r++) {
-    if (val(r, 0) != inf) {
-      const double f = fac[r];
-      S = fma(val(r, 1), f, S); A = fma(val(r, 2), f, A); B = fma(val(r, 3), f, B);
+  m = inf; S = A = B = DL = DR = 0.0;
+  for (int r0 = 0; r0 < a.nranks; r0 += 32) {
+    const int r = r0 + lane;
+    double v[6] = {inf, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (r < a.nranks) {
+      const MppiLL *src = reinterpret_cast<const MppiLL *>(a.peer[a.rank]) + (((size_t)par * a.nranks + r) * T + t) * 3;
+      unsigned polls = 0;
+      for (;;) {
+        bool ok = mppi_ll_load_sys(src, a.call_id, v[0], v[1]);
+        ok &= mppi_ll_load_sys(src + 1, a.call_id, v[2], v[3]);
+        ok &= mppi_ll_load_sys(src + 2, a.call_id, v[4], v[5]);
+        if (ok) break;
+        if (++polls == (1u << 27)) __trap();          // about a minute without the peer's words: fail loudly, not silently
+      }
     }
-    DL += val(r, 4); DR += val(r, 5);
+    __syncwarp();
+    // this group of (up to) 32 ranks into the running result: minimum first, every rank rescaled once
+    const double mn = mppi_min(m, warp_min(v[0]));
+    if (mn != inf) {
+      const double f = (v[0] == inf) ? 0.0 : (v[0] == mn) ? 1.0 : mppi_exp_neg<FASTEXP>((mn - v[0]) * a.inv_lambda);
+      const double fo = (m == inf) ? 0.0 : (m == mn) ? 1.0 : mppi_exp_neg<FASTEXP>((mn - m) * a.inv_lambda);
+      S = fma(S, fo, warp_sum(v[1] * f)); A = fma(A, fo, warp_sum(v[2] * f)); B = fma(B, fo, warp_sum(v[3] * f));
+    }
+    DL += warp_sum(v[4]); DR += warp_sum(v[5]);
+    m = mn;
   }
+  mppi_stamp(a, 7);
 }
 
 // merge of one step's partials by one CTA of NT threads: minimum first, then every partial rescaled once (independent
@@ -742,9 +751,24 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
 
   // launched programmatically dependent on the previous call: everything above overlapped its tail; the plan it writes
   // is read from here on
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // the variates of the first pass: in flight while this CTA waits for the plan (the grid in front - the noise kernel - is
-  // complete from here on)
+  if (!a.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  else if (z_ahead) {
+    // not the grids in front, only what this call reads from them: the variates (drawn two calls ahead: long there) and,
+    // below, the plan.  One thread watches the count (a single word polled by every warp of every CTA would starve the
+    // reductions that advance it); its acquire load and the barrier order the CTA's ordinary loads behind the noise kernel
+    if (threadIdx.x == 0) {
+      unsigned long long seen;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.z_ready) : "memory");
+        if (seen >= a.z_need) break;
+        if (++spins == (1u << 26)) __trap();
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  // the variates of the first pass: in flight while this CTA waits for the plan
   float4 zn[FAST ? S / 2 : 1];
   if (z_ahead && base < a.K) {
     const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
@@ -1132,6 +1156,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
 // last passes, the merge tree - runs on a few CTAs), and in a control loop it runs while the host turns the pose around.
 struct MppiNoiseArgs
 {
+  unsigned long long *z_ready;   // CTAs of noise kernels that have finished (MppiArgs::z_ready)
   float4 *zbuf;
   int K, half_T, k_offset;
   uint32_t call;
@@ -1160,6 +1185,9 @@ __global__ void __launch_bounds__(256) mppi_noise_kernel(const __grid_constant__
     box_muller_f32(c2, c3, z.z, z.w);
     n.zbuf[i] = z;
   }
+  // count this CTA's share in (a release by one thread after the barrier covers every thread's stores)
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(n.z_ready), "l"(1ull) : "memory");
 }
 
 // ---- the update as a separate kernel: the NCCL transport of a sharded job and the partials tap -------------------------

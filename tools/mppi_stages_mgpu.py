@@ -55,6 +55,8 @@ for mode in ("synchronous", "pipelined"):
             row[names[j]] = (d[:-T, j].max() - t0) / 1e3
         for j in (4, 5, 7, 6):
             row[names[j]] = ((mg[:, j].min() - t0) / 1e3, (np.median(mg[:, j]) - t0) / 1e3, (mg[:, j].max() - t0) / 1e3)
+        row["prev updated (max) -> this loop start (min)"] = (t0 - mg[:, 12].max()) / 1e3
+        row["period (loop start to loop start, median)"] = float(np.median(d[:-T, 0] - d[:-T, 11])) / 1e3
         row["merged->received (median over steps)"] = float(np.median(mg[:, 7] - mg[:, 5])) / 1e3
         row["received->updated"] = float(np.median(mg[:, 6] - mg[:, 7])) / 1e3
         lines.append(row)
