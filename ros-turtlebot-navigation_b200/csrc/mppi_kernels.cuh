@@ -13,24 +13,30 @@
 //     Taylor series of the half-step angle - no full-range sincos anywhere), the position a prefix sum of
 //     increments, the cost-to-go a suffix sum (cumSumCost).  All in fp64 registers - the shipped cost
 //     weights (Q = 1e4, lambda = 0.01) make the softmax ill-conditioned in anything narrower.
-//   * noise is counter-based (Philox4x32-10 keyed by seed, call, rollout, step pair) and generated in
-//     registers: one Philox call feeds four binary32 Box-Muller variates (two steps x two wheels) built
-//     from correctly-rounded operations only, so the CPU oracle reproduces them bit for bit.
+//   * noise is counter-based (Philox4x32-10 keyed by seed, call, rollout, step pair): one Philox call feeds four binary32
+//     Box-Muller variates (two steps x two wheels) built from correctly-rounded operations only, so the CPU oracle
+//     reproduces them bit for bit.  The production variants LOAD them: mppi_noise_kernel draws a call's variates two calls
+//     ahead, in the tail of an earlier call; the generic variant (taps, caller-supplied noise, ragged horizons) draws them
+//     in the loop.
 //   * the only mandatory HBM traffic is the fp32 [K][T][3] state tensor: each warp stages its rows in
-//     shared memory and one lane hands them to the TMA unit (cp.async.bulk shared->global), double
-//     buffered so the next rollouts' math overlaps the store.
-//   * the T softmaxes are carried ONLINE: every lane keeps (min J, sum e, sum e*duL, sum e*duR) for its S steps in
-//     shared memory and only touches them when a rollout's cost-to-go comes within the exponent range of the lane's
-//     running minimum (a one-instruction integer test on the high word against a threshold held in a register);
-//     sum duL, sum duR live in registers.  J never makes a round trip through HBM.
+//     shared memory and one lane hands them to the TMA unit (cp.async.bulk shared->global), so the next rollouts' math
+//     overlaps the store.
+//   * the T softmaxes are carried ONLINE, (min J, sum e, sum e*duL, sum e*duR) per lane and step in shared memory.
+//     Production variants park the cost-to-go of three passes by step and update the sets once per batch - minimum first,
+//     then every weight independently through the SFU in binary32 (the exponent difference is formed in fp64), straight-
+//     line code; the generic variant updates rollout by rollout in fp64 behind a threshold test on the high word of J.
+//     J never makes a round trip through HBM.
 //   * THE CALL IS ONE LAUNCH.  The grid is the rollout CTAs followed by T MERGER CTAs.  Every rollout CTA merges its warps
-//     into one [T][6] partial and counts itself in (a release reduction, nothing to wait for).  The merger CTAs carry the
-//     highest block indices, so they take the SM slots the first rollout CTAs leave; merger t waits for the count, merges
-//     step t's partials of all CTAs (minimum first, every partial rescaled once, fixed order: bit-reproducible), exchanges
-//     the result with the other ranks over NVLink peer memory when the job is sharded, applies the update of
-//     mppi.cpp:112-137 and publishes the first control in mapped pinned host memory.  (A two-level "last arriver merges"
-//     tree inside the rollout CTAs was built first and measured 3x slower: two fence + atomic + dependent-load rounds in
-//     series on ONE CTA against T CTAs working side by side.)
+//     into one [T][6] partial and sends it to the mergers as TAGGED WORDS (32 bytes = two doubles in four 8-byte units, each
+//     4 bytes of payload next to the call's tag: a unit that shows the tag is its payload, so nothing has to be ordered -
+//     no release / acquire pair, no fence; NCCL's LL protocol on L2).  The merger CTAs carry the highest block indices, so
+//     they take the SM slots the first rollout CTAs leave; merger t merges step t's partials of all CTAs (minimum first,
+//     every partial rescaled once, fixed order: bit-reproducible), exchanges the result with the other ranks over NVLink
+//     peer memory when the job is sharded (same words, system scope), applies the update of mppi.cpp:112-137, leaves the
+//     plan's step as a tagged word for the next call's CTAs and publishes the first control in mapped pinned host memory.
+//     A call queued behind an uncollected call waits for those words and for the variates' count, not for the grids in
+//     front of it (MppiArgs::skip_wait).  (A two-level "last arriver merges" tree inside the rollout CTAs was built first
+//     and measured 3x slower: two fence + atomic + dependent-load rounds in series on ONE CTA against T CTAs side by side.)
 #pragma once
 
 #include "common.cuh"
