@@ -93,6 +93,8 @@ struct b2n_mppi
   std::vector<cudaEvent_t> ev;           // start/stop pairs
   size_t ev_used = 0;
   bool pending = false;
+  bool prof = false;                     // B2N_MPPI_HOST_BREAKDOWN=1: host time per phase of a synchronous call (tuning)
+  double prof_ns[4] = {0, 0, 0, 0};      //   arguments, the call's launch, the noise kernel's launch, wait for the controls
   unsigned long long waited_seq = 0;     // sequence number of the last call whose controls b2n_mppi_wait handed out
 };
 
@@ -335,6 +337,9 @@ int launch_update(b2n_mppi *h, const MppiUpdateArgs &u)
 int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behind = true)
 {
   const b2n_mppi_params &p = h->p;
+  using clk = std::chrono::steady_clock;
+  clk::time_point pt0, pt1, pt2;
+  if (h->prof) pt0 = clk::now();
   MppiArgs a = make_args(h, x, y, theta);
   h->last_slot = h->ring_pos;
   a.states = h->d_states + (size_t)h->ring_pos * h->K * h->T * 3;
@@ -364,10 +369,12 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behin
     h->ev_used += 2;
     B2N_CUDA(cudaEventRecord(e0, h->stream));
   }
+  if (h->prof) pt1 = clk::now();
   launch_rollout(h, a, variant);
   B2N_CUDA(cudaGetLastError());
   if (e1) B2N_CUDA(cudaEventRecord(e1, h->stream));
   h->launches++;
+  if (h->prof) pt2 = clk::now();
 
   if (nccl_transport) {
     // baseline transport of a sharded job: local merge -> one allgather of [T][6] doubles -> identical update on every
@@ -406,6 +413,11 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behin
     // (h->call is the NEXT call by now: its variates are normally there already, drawn behind the call before this one)
     for (uint32_t ahead_by = 0; ahead_by < 2; ahead_by++)
       if (int rc = ensure_noise(h, h->call + ahead_by, (h->zslot + (int)ahead_by) % kZBuf, !nccl_transport)) return rc;
+  }
+  if (h->prof) {
+    h->prof_ns[0] += std::chrono::duration<double, std::nano>(pt1 - pt0).count();
+    h->prof_ns[1] += std::chrono::duration<double, std::nano>(pt2 - pt1).count();
+    h->prof_ns[2] += std::chrono::duration<double, std::nano>(clk::now() - pt2).count();
   }
   return B2N_OK;
 }
@@ -893,11 +905,20 @@ int b2n_mppi_time_new_controls(b2n_mppi *h, double x, double y, double theta, in
 {
   B2N_REQUIRE(h && avg_ms && calls > 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
   double l = 0.0, r = 0.0;
+  h->prof = std::getenv("B2N_MPPI_HOST_BREAKDOWN") != nullptr;
+  for (double &v : h->prof_ns) v = 0.0;
   const auto t0 = std::chrono::steady_clock::now();
   for (int i = 0; i < calls; i++)
     if (int rc = b2n_mppi_new_controls(h, x, y, theta, &l, &r)) return rc;
   const auto t1 = std::chrono::steady_clock::now();
   *avg_ms = std::chrono::duration<double, std::milli>(t1 - t0).count() / calls;
+  if (h->prof) {
+    const double total = std::chrono::duration<double, std::nano>(t1 - t0).count();
+    std::fprintf(stderr, "host time per synchronous call: arguments %.2f us, launch of the call %.2f us, launch of the noise kernel %.2f us, rest (wait for the controls) %.2f us; total %.2f us\n",
+                 h->prof_ns[0] / calls / 1e3, h->prof_ns[1] / calls / 1e3, h->prof_ns[2] / calls / 1e3,
+                 (total - h->prof_ns[0] - h->prof_ns[1] - h->prof_ns[2]) / calls / 1e3, total / calls / 1e3);
+    h->prof = false;
+  }
   if (ul) *ul = l;
   if (ur) *ur = r;
   return B2N_OK;

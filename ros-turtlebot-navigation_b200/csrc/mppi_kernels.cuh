@@ -701,6 +701,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  mppi_stamp(a, 13);               // (tuning runs) the CTA's first instruction
   const int g = lane & (G - 1);    // position inside the rollout's lane group
   const int r = lane / G;          // which of the warp's R rollouts
   // warp-major numbering of the grid's warps: the last, partly filled round of passes then spreads over ALL CTAs (the first
