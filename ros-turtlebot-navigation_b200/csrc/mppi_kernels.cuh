@@ -110,8 +110,8 @@ struct MppiArgs
   unsigned long long seq;
   double *stepstats;       // [T][2] (min J, sum w) for the weights tap
   double *merged;          // [T][6] this rank's merged sums (tap)
-  unsigned long long *dbg;       // [grid][8] stage timestamps (globaltimer ns) of every CTA's thread 0, tuning runs only (null: off)
-  // sharded job: peer-memory exchange areas [2 parities][nranks][T][12 words], see mppi_exchange()
+  unsigned long long *dbg;       // [grid + T][kMppiDbgSlots] stage timestamps (globaltimer ns) of every CTA's thread 0, tuning runs only (null: off)
+  // sharded job: peer-memory exchange areas [2 parities][nranks][T][3 tagged 32-byte words], see mppi_exchange_step()
   int rank, nranks, parity;
   uint32_t call_id;
   unsigned long long *peer[kMppiMaxRanks];

@@ -1,4 +1,8 @@
-"""Tuning: where one MPPI call spends its time (stage stamps of every CTA, B2N_MPPI_DEBUG_TIMES=1)."""
+"""Tuning: where one MPPI call spends its time (globaltimer stamps of every CTA's thread 0, B2N_MPPI_DEBUG_TIMES=1).
+  python tools/mppi_stages.py [K] [horizon]
+Stamps are microseconds from the first CTA's first instruction.  Rollout CTAs: entry, loop start, loop end (the stamp sits
+behind a barrier that defers blocking: it is when warp 0 arrived), sets merged, partial words sent, landed (read back from
+L2).  Merger CTAs: resident, partials in, merged, (sharded: received), updated."""
 import os
 import sys
 
@@ -19,30 +23,31 @@ m.setStateRing(16)
 m.seed(42)
 m.setWaypoint(pkg.Pose(theta=1.5707, x=1.0, y=0.0))
 pose = pkg.Pose(theta=0.0, x=0.0, y=0.0)
-names = ["loop start", "loop end", "partial written", "merger: partials in", "merger: resident", "merger: merged", "merger: updated", "-"]
-for rep in range(6):
+ROLL = [(13, "entry"), (0, "loop start"), (1, "loop end"), (3, "sets merged"), (2, "partial sent"), (7, "landed + read back")]
+MERG = [(4, "resident"), (3, "partials in"), (5, "merged"), (6, "updated")]
+
+
+def show(tag):
+    d = m.debugTimes().astype(np.int64)
+    T = m.steps
+    r, g = d[:-T], d[-T:]
+    e0 = r[:, 13].min()
+    f = lambda c: "%6.2f .. %6.2f .. %6.2f" % ((c.min() - e0) / 1e3, (np.median(c) - e0) / 1e3, (c.max() - e0) / 1e3)
+    print("%s: %d rollout CTAs + %d merger CTAs (min .. median .. max, us)" % (tag, r.shape[0], T))
+    for j, n in ROLL:
+        print("  rollout CTAs  %-20s %s" % (n, f(r[:, j])))
+    for j, n in MERG:
+        print("  merger CTAs   %-20s %s" % (n, f(g[:, j])))
+    print("  previous call's last update -> this call's first loop start %.2f us; period (loop start to loop start, median) %.2f us"
+          % ((r[:, 0].min() - g[:, 12].max()) / 1e3, np.median(r[:, 0] - r[:, 11]) / 1e3))
+
+
+for rep in range(3):
     for _ in range(10):
         m.newControls(pose)
-    d = m.debugTimes().astype(np.int64)
-    t0 = d[:-m.steps, 0].min()
-    print("call %d: grid %d" % (rep, d.shape[0]))
-    for j, n in enumerate(names):
-        col = d[:, j]
-        ok = col >= t0
-        col = col[ok] - t0
-        if len(col):
-            print("  %-16s n=%4d  min %7.2f  median %7.2f  max %7.2f us" % (n, len(col), col.min() / 1e3, np.median(col) / 1e3, col.max() / 1e3))
-    # per-CTA stage durations
-    for i, j in ((0, 1), (1, 2), (4, 3), (3, 5), (5, 6)):
-        ok = (d[:, j] >= t0) & (d[:, i] >= t0)
-        if ok.any():
-            dd = (d[ok, j] - d[ok, i]) / 1e3
-            print("  %-16s -> %-16s n=%4d  min %6.2f median %6.2f max %6.2f us" % (names[i], names[j], ok.sum(), dd.min(), np.median(dd), dd.max()))
-    ph = ["z load", "D sums", "(decl)", "local integration", "rot scan", "pos scan", "stage wait", "loss + stores", "cost scan", "softmax", "bulk store"]
-    c = d[:-m.steps, 8:19]
-    dc = np.diff(c, axis=1)
-    print("  first pass of warp 0, SM cycles per phase (median over CTAs | CTA 0):")
-    for j, n in enumerate(ph[1:] + ["?"]):
-        if j < dc.shape[1]:
-            print("    %-20s %8.0f | %8d" % (ph[j] if j == 0 else ph[j], np.median(dc[:, j]), dc[0, j]))
-    print("    total pass           %8.0f" % np.median(c[:, -1] - c[:, 0]))
+    show("synchronous calls, run %d" % rep)
+for rep in range(3):
+    for _ in range(100):
+        m.enqueue(pose)
+    m.wait()
+    show("queued calls, run %d" % rep)
