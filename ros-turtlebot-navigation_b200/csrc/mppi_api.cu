@@ -93,6 +93,7 @@ struct b2n_mppi
   std::vector<cudaEvent_t> ev;           // start/stop pairs
   size_t ev_used = 0;
   bool pending = false;
+  bool obs_external = false;             // the obstacle field's device address is known to a producer outside this handle
   bool prof = false;                     // B2N_MPPI_HOST_BREAKDOWN=1: host time per phase of a synchronous call (tuning)
   double prof_ns[4] = {0, 0, 0, 0};      //   arguments, the call's launch, the noise kernel's launch, wait for the controls
   unsigned long long waited_seq = 0;     // sequence number of the last call whose controls b2n_mppi_wait handed out
@@ -355,13 +356,14 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behin
   const bool nccl_transport = h->nranks > 1 && !h->p2p_ready;
   if (!nccl_transport) arm_tail(h, a);      // the whole call is this one launch
   // a fused call behind a fused call reads two things from the grids in front of it - the variates and the plan - and
-  // waits for exactly those (MppiArgs::skip_wait).  Any other device-resident input (the obstacle field may be rewritten
-  // in place by work on this stream) keeps the wait for the grids themselves
+  // waits for exactly those (MppiArgs::skip_wait).  Any other device-resident input keeps the wait for the grids themselves:
+  // an obstacle field whose device address was handed out (b2n_mppi_obstacle_field_device) may be rewritten in place by
+  // work on this stream; one copied from the host (b2n_mppi_set_obstacle_field) cannot change under a queued call
   a.z_ready = h->d_zready; a.z_need = h->z_ready_at[h->zslot];
   // ... and only when calls are being queued up (the previous call's controls have not been collected): behind a call the
   // host has already waited for, the grids in front are complete and the plain wait costs nothing (measured 0.4 us less
   // than the count's round trip)
-  a.skip_wait = (ahead && a.tail && a.plan_tag != 0 && !a.obs_on && h->use_pdl && !h->full_wait && h->waited_seq + 1 != a.seq) ? 1 : 0;
+  a.skip_wait = (ahead && a.tail && a.plan_tag != 0 && !(a.obs_on && h->obs_external) && h->use_pdl && !h->full_wait && h->waited_seq + 1 != a.seq) ? 1 : 0;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->ev_used + 2 <= h->ev.size()) {
@@ -746,6 +748,7 @@ int b2n_mppi_set_obstacle_field(b2n_mppi *h, const float *dist, int xsize, int y
   B2N_CUDA(cudaStreamSynchronize(h->stream));
   h->obs_on = 1; h->obs_xsize = xsize; h->obs_ysize = ysize; h->obs_xmin = xmin; h->obs_ymin = ymin;
   h->obs_res = resolution; h->obs_weight = weight; h->obs_d0 = d0; h->obs_off = off_map;
+  h->obs_external = false;
   return B2N_OK;
 }
 
@@ -766,6 +769,7 @@ int b2n_mppi_obstacle_field_device(b2n_mppi *h, int xsize, int ysize, double xmi
   h->obs_on = 1; h->obs_xsize = xsize; h->obs_ysize = ysize; h->obs_xmin = xmin; h->obs_ymin = ymin;
   h->obs_res = resolution; h->obs_weight = weight; h->obs_d0 = d0; h->obs_off = off_map;
   *device_field = h->d_obs;
+  h->obs_external = true;
   return B2N_OK;
 }
 

@@ -333,20 +333,41 @@ def test_set_initial_controls_fills_plan_and_tail(gpu_pkg):
     assert p[0, -1] == 1.5 and p[1, -1] == -0.5          # mppi.cpp:136-137
 
 
-def test_async_queue_equals_synchronous_calls(gpu_pkg):
-    a = make_gpu(gpu_pkg, 0.64, 0.01, 256)
-    b = make_gpu(gpu_pkg, 0.64, 0.01, 256)
+@pytest.mark.parametrize("K,obstacles,calls", [(256, False, 5), (4096, False, 40), (2048, True, 24)])
+def test_async_queue_equals_synchronous_calls(gpu_pkg, K, obstacles, calls):
+    """Queued calls (which wait for the previous call's plan words and for the variates' count instead of for the grids in
+    front of them, with the variates drawn two calls ahead into three rotating buffers) against synchronous calls: the same
+    controls and plan bit for bit, and both equal to the oracle's - also with the obstacle term (field copied from the host)."""
+    a = make_gpu(gpu_pkg, 0.64, 0.01, K)
+    b = make_gpu(gpu_pkg, 0.64, 0.01, K)
+    o = orc.OracleMppi(0.64, 0.01, K)
     P = gpu_pkg.Pose(theta=0.2, x=0.1, y=-0.1)
+    xs = np.arange(200)
+    dist = np.hypot((xs[:, None] - 108) * 0.05, (xs[None, :] - 99) * 0.05).astype(np.float32)   # one obstacle cell near the path
     for m in (a, b):
         m.seed(11)
         m.setWaypoint(gpu_pkg.Pose(theta=0.0, x=1.0, y=0.0))
-    for _ in range(5):
+        if obstacles:
+            m.setObstacleField(dist, -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+    o.noise_philox(11)
+    o.setWaypoint(1.0, 0.0, 0.0)
+    if obstacles:
+        o.set_obstacles(dist, -5.0, -5.0, 0.05, 5e4, 0.4, 1e6)
+    for _ in range(calls):
         va = a.newControls(P)
-    for _ in range(5):
+    for _ in range(calls):
         b.enqueue(P)
     vb = b.wait()
+    assert a.lastVariant() == "fast" and b.lastVariant() == "fast"
     assert (va.ul, va.ur) == (vb.ul, vb.ur)
     assert np.array_equal(a.plan(), b.plan())
+    assert np.array_equal(a.states(), b.states())
+    for _ in range(calls):
+        co = o.newControls(0.1, -0.1, 0.2)
+    assert rel_err([vb.ul, vb.ur], co, 1e-3) < RTOL
+    # (entries of the plan that happen to lie near zero are held to 1e-5 of 0.1 rad/s, not of themselves: after two dozen
+    # receding-horizon calls the binary32 weights of the production variant have moved them by some 1e-7 of the control scale)
+    assert rel_err(b.plan(), o.get()["plan"], 0.1) < RTOL
 
 
 def test_state_ring_and_launch_count(gpu_pkg):
