@@ -442,8 +442,7 @@ def c4_leg(pkg, torch, dist, rank, world, local, exchange, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        for _ in range(n):
-            m.enqueue(pose)
+        m.enqueueMany(pose, n)
         e1.record(stream)
         m.wait()
         torch.cuda.synchronize()
@@ -609,8 +608,7 @@ def run_ours(args):
     # steps the pipelined path runs untimed for RAMP_CALLS calls (about half a second); the W warm-up steps and the K
     # timed steps follow.
     for _ in range(0 if args.no_ramp else RAMP_CALLS // 256):   # a fixed COUNT: sharded ranks must make the same number of calls
-        for _ in range(256):
-            mppi.enqueue(pose)
+        mppi.enqueueMany(pose, 256)
         mppi.wait()
     for _ in range(max(args.warmup, 3)):
         mppi.newControls(pose)
@@ -624,8 +622,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        mppi.enqueue(pose)
+    mppi.enqueueMany(pose, args.steps)          # one C loop over the C ABI: no interpreter (or clock-sampler thread) between two launches
     e1.record(stream)
     mppi.wait()
     barrier()

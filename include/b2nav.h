@@ -79,6 +79,9 @@ int b2n_mppi_new_controls(b2n_mppi *h, double x, double y, double theta, double 
  * the most recently enqueued call is done and returns its controls. */
 int b2n_mppi_enqueue(b2n_mppi *h, double x, double y, double theta);
 int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur);
+/* `calls` times b2n_mppi_enqueue() with the same pose from one C loop (what a C++ caller's loop does; the bench's
+ * device-resident leg uses it so that no interpreter sits between two launches) */
+int b2n_mppi_enqueue_many(b2n_mppi *h, double x, double y, double theta, int calls);
 
 /* Noise.  The reference draws from one process-global std::mt19937_64 (rigid2d/src/rigid2d/
  * utilities.cpp:12-24); a serial engine cannot feed K*T lanes, so the kernels use a counter-based
@@ -121,8 +124,8 @@ int b2n_mppi_launch_count(const b2n_mppi *h, uint64_t *launches);
 /* *fast = 1 when the last call ran the production (FAST) instantiation of the kernel, 0 for the generic one (capture taps,
  * caller-supplied noise, horizons that leave lanes partially filled): lets a parity test prove which one it checked */
 int b2n_mppi_last_variant(const b2n_mppi *h, int *fast);
-/* tuning hook (B2N_MPPI_DEBUG_TIMES=1 at create): globaltimer stamps [grid][8] of every CTA of the last call: loop start, loop end,
- * CTA partial written, group ticket drawn, group merged, grid ticket drawn, grid merged, plan published (0 where a CTA left earlier) */
+/* tuning hook (B2N_MPPI_DEBUG_TIMES=1 at create): globaltimer stamps [grid + T][24] of thread 0 of every CTA of the last call
+ * (rollout CTAs, then the T merger CTAs); the slots are listed in tools/mppi_stages.py */
 int b2n_mppi_debug_times(b2n_mppi *h, unsigned long long *out, size_t count, int *grid);
 /* test hook: the Box-Muller stage of the perturbation generator alone, z[2 i], z[2 i + 1] for the first words
  * (first + i) << 9, i < count (the 2^23 values cover every radius the generator can produce) and one second word rb */

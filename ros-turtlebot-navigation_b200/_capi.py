@@ -59,6 +59,7 @@ PROTOTYPES = {
     "b2n_mppi_set_waypoint": (C.c_int, [_vp, D, D, D]),
     "b2n_mppi_new_controls": (C.c_int, [_vp, D, D, D, _P(D), _P(D)]),
     "b2n_mppi_enqueue": (C.c_int, [_vp, D, D, D]),
+    "b2n_mppi_enqueue_many": (C.c_int, [_vp, D, D, D, C.c_int]),
     "b2n_mppi_wait": (C.c_int, [_vp, _P(D), _P(D)]),
     "b2n_mppi_seed": (C.c_int, [_vp, C.c_uint64, C.c_uint32]),
     "b2n_mppi_set_noise": (C.c_int, [_vp, _vp, _sz]),

@@ -85,6 +85,10 @@ class MPPI:
     def enqueue(self, ps):
         _capi.check(self._lib.b2n_mppi_enqueue(self._h, ps.x, ps.y, ps.theta))
 
+    def enqueueMany(self, ps, calls):
+        """`calls` queued calls with the same pose from one C loop"""
+        _capi.check(self._lib.b2n_mppi_enqueue_many(self._h, ps.x, ps.y, ps.theta, int(calls)))
+
     def wait(self):
         ul, ur = C.c_double(), C.c_double()
         _capi.check(self._lib.b2n_mppi_wait(self._h, C.byref(ul), C.byref(ur)))

@@ -575,6 +575,15 @@ int b2n_mppi_enqueue(b2n_mppi *h, double x, double y, double theta)
   return enqueue_call(h, x, y, theta);
 }
 
+int b2n_mppi_enqueue_many(b2n_mppi *h, double x, double y, double theta, int calls)
+{
+  B2N_REQUIRE(h && calls >= 0, B2N_ERR_INVALID_ARGUMENT, "bad argument");
+  if (int rc = set_device(h)) return rc;
+  for (int i = 0; i < calls; i++)
+    if (int rc = enqueue_call(h, x, y, theta)) return rc;
+  return B2N_OK;
+}
+
 int b2n_mppi_wait(b2n_mppi *h, double *ul, double *ur)
 {
   B2N_REQUIRE(h, B2N_ERR_INVALID_ARGUMENT, "null handle");
