@@ -157,7 +157,10 @@ int b2n_mppi_p2p_export(b2n_mppi *h, int nranks, void *handle64);
 int b2n_mppi_p2p_init(b2n_mppi *h, int rank, int nranks, const void *handles);
 /* The same wiring for ranks that are handles of ONE process (several GPUs driven by one process, or - in the tests - two
  * ranks sharing one GPU on separate streams): b2n_mppi_p2p_export on every handle, then the device addresses of all
- * areas (b2n_mppi_p2p_area) in rank order.  The handles must outlive each other's use. */
+ * areas (b2n_mppi_p2p_area) in rank order.  The handles must outlive each other's use.  Ranks that SHARE a GPU must
+ * collect every call (b2n_mppi_wait) before enqueuing the next one: the merger CTAs of a call spin while resident, waiting
+ * for the other ranks' words, and a queued next call of one rank could take the SM slots another rank's mergers still need.
+ * With one GPU per rank (the supported deployment) calls may be queued freely. */
 int b2n_mppi_p2p_area(b2n_mppi *h, void **area);
 int b2n_mppi_p2p_init_local(b2n_mppi *h, int rank, int nranks, void *const *areas);
 
