@@ -409,9 +409,9 @@ int enqueue_call(b2n_mppi *h, double x, double y, double theta, bool noise_behin
   h->zslot = (h->zslot + 1) % kZBuf;
   h->ext_armed = false;
   h->pending = true;
-  // the next call's variates, behind this call: off the next call's critical path
+  // the variates of the call after the next one, behind this call: off every call's critical path
   if (ahead && h->noise_ahead && noise_behind) {
-    // (behind a fused call only: that call's successor finds the plan through its sequence word, not through this grid)
+    // (with programmatic launch behind a fused call only: that call's successor finds the plan through its tagged words, not through this grid)
     // (h->call is the NEXT call by now: its variates are normally there already, drawn behind the call before this one)
     for (uint32_t ahead_by = 0; ahead_by < 2; ahead_by++)
       if (int rc = ensure_noise(h, h->call + ahead_by, (h->zslot + (int)ahead_by) % kZBuf, !nccl_transport)) return rc;

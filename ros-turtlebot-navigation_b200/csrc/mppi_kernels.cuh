@@ -606,8 +606,8 @@ template <int NT, bool FASTEXP>
 __device__ __forceinline__ void mppi_merger(const MppiArgs &a)
 {
   const int t = (int)blockIdx.x - a.n_roll;
-  // this step of the current plan: fetched now, used after the wait (the plan does not change during the call)
-  // (a merger can be resident before the previous call has finished: the plan's step count first, as the rollout CTAs do)
+  // this step of the current plan: fetched now, used after the merge (the plan does not change during the call; a merger
+  // can be resident before the previous call has written it: the tagged word says when it is there, as for the rollout CTAs)
   double ul_cur = 0.0, ur_cur = 0.0;
   if (threadIdx.x == 0) {
     if (a.plan_tag) mppi_ll_wait(a.ll_plan + t, a.plan_tag, ul_cur, ur_cur);
@@ -1173,8 +1173,9 @@ struct MppiNoiseArgs
 __global__ void __launch_bounds__(256) mppi_noise_kernel(const __grid_constant__ MppiNoiseArgs n)
 {
   // the kernel behind this one (the next call) may be scheduled as soon as SMs free up; it waits for this grid's completion
-  // and, through the plan's sequence word, for the call in front of this grid.  No wait here: the buffer written was last
-  // read two calls ago, and a grid that blocks while resident could starve another rank sharing the GPU
+  // (or, queued, for the count at the end of this kernel) and, through the plan's tagged words, for the call in front of
+  // this grid.  No wait here: the buffer written was last read three calls ago, and a grid that blocks while resident could
+  // starve another rank sharing the GPU
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const size_t total = (size_t)n.K * n.half_T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
