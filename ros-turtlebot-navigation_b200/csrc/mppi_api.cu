@@ -288,7 +288,10 @@ int ensure_noise(b2n_mppi *h, uint32_t call, int slot, bool pdl)
   B2N_REQUIRE(h->d_z[slot], B2N_ERR_CUDA, "no buffer for the variates (the horizon does not fit a production shape)");
   MppiNoiseArgs na;
   std::memset(&na, 0, sizeof(na));
-  na.z_ready = h->d_zready; na.zbuf = h->d_z[slot]; na.K = h->K; na.half_T = h->T / 2; na.k_offset = h->p.rollout_offset; na.call = call;
+  na.z_ready = h->d_zready; na.zbuf = h->d_z[slot]; na.K = h->K; na.half_T = h->T / 2;
+  na.half_shift = -1;
+  for (int s = 0; s < 30; s++) if ((1 << s) == na.half_T) na.half_shift = s;
+  na.k_offset = h->p.rollout_offset; na.call = call;
   for (int r = 0; r < 10; r++) {
     na.key0[r] = (uint32_t)h->seed + (uint32_t)r * 0x9E3779B9u;
     na.key1[r] = (uint32_t)(h->seed >> 32) + (uint32_t)r * 0xBB67AE85u;

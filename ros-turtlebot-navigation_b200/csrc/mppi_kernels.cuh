@@ -1166,6 +1166,7 @@ struct MppiNoiseArgs
   unsigned long long *z_ready;   // CTAs of noise kernels that have finished (MppiArgs::z_ready)
   float4 *zbuf;
   int K, half_T, k_offset;
+  int half_shift;                // log2(half_T) when it is a power of two (the usual horizons), else -1: spares a 64-bit division per element
   uint32_t call;
   uint32_t key0[10], key1[10];
 };
@@ -1179,7 +1180,8 @@ __global__ void __launch_bounds__(256) mppi_noise_kernel(const __grid_constant__
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const size_t total = (size_t)n.K * n.half_T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t k = (uint32_t)(i / n.half_T), idx = (uint32_t)(i - (size_t)k * n.half_T);
+    const uint32_t k = n.half_shift >= 0 ? (uint32_t)(i >> n.half_shift) : (uint32_t)(i / n.half_T);
+    const uint32_t idx = (uint32_t)(i - (size_t)k * n.half_T);
     uint32_t c0 = idx, c1 = (uint32_t)n.k_offset + k, c2 = n.call, c3 = kDomainMppi;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
