@@ -136,6 +136,22 @@ struct MppiUpdateArgs
 // minimum of two costs (never NaN): a compare and a select, where fmin spends half a dozen instructions on NaN rules
 __device__ __forceinline__ double mppi_min(double a, double b) { return b < a ? b : a; }
 
+// A load of the variates' buffer.  Through the read-only path (ld.global.nc) by default: it runs beside the load / store unit,
+// which the shared-memory traffic of the loop keeps busy (measured on one box: rollout phase 12.62 us against 12.76 us with
+// plain loads, a queued call 16.37 against 16.53 us).  The path is specified for data that nobody writes while the kernel
+// lives; what makes it safe here: the buffer a call reads was filled two calls earlier by a kernel that has completed
+// before this grid reads a single word of it (griddepcontrol.wait, or the acquire load of the finished-CTA count, both of
+// which also drop what the SM's L1 holds), the kernels that run beside this one write the OTHER two buffers of the rotation,
+// and no CTA touches the buffer before that wait.  -DB2N_MPPI_Z_PLAIN_LOADS selects ordinary loads.
+__device__ __forceinline__ float4 mppi_z_load(const float4 *p)
+{
+#ifdef B2N_MPPI_Z_PLAIN_LOADS
+  return *p;
+#else
+  return __ldg(p);
+#endif
+}
+
 // tagged 32-byte words (see MppiArgs::ll_partials): two doubles, each 4-byte half next to the tag in its own 8-byte unit.
 // One 256-bit store writes a whole 32-byte sector (a narrower store would leave a partially valid sector in L2, and the
 // reader's load would then wait for the rest of it from DRAM)
@@ -780,7 +796,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
   if (z_ahead && base < a.K) {
     const float4 *zr = a.zbuf + ((size_t)min(base + r, a.K - 1) * (TP / 2) + (t0 >> 1));
 #pragma unroll
-    for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
+    for (int s = 0; s < S; s += 2) zn[s / 2] = mppi_z_load(zr + s / 2);
   }
   // the obstacle-field tile around the start pose (occupancy-grid tiles staged through TMA, north_star): rows of the tile
   // are contiguous in the field, one bulk copy each, all completing on one mbarrier.  After the wait: the field may have
@@ -835,7 +851,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
         const int kk = kb[p] + r;
         const bool on = p < np && kk < a.K;
         Jc[p] = on ? jb[(size_t)p * R * TP + ts] : inf;
-        const float4 q = __ldg(a.zbuf + ((size_t)(on ? kk : 0) * (TP / 2) + (ts >> 1)));
+        const float4 q = mppi_z_load(a.zbuf + ((size_t)(on ? kk : 0) * (TP / 2) + (ts >> 1)));
         zc[p] = (g & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
       }
       double M = m0;
@@ -1001,7 +1017,7 @@ __global__ void __launch_bounds__(NW * 32, mppi_min_blocks(S, NW)) mppi_rollout_
       // the next pass's variates: in flight during the scan and the softmax below
       const float4 *zr = a.zbuf + ((size_t)min(base + nw * R + r, a.K - 1) * (TP / 2) + (t0 >> 1));
 #pragma unroll
-      for (int s = 0; s < S; s += 2) zn[s / 2] = __ldg(zr + s / 2);
+      for (int s = 0; s < S; s += 2) zn[s / 2] = mppi_z_load(zr + s / 2);
     }
     // ---- cost-to-go: segmented suffix sum over the lanes ---------------------------------------------------
     double ij = rj;
