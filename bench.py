@@ -648,7 +648,7 @@ def run_ours(args):
     # ---- roofline pass: the rollout kernel alone, launched back to back between two CUDA events on the ------
     # handle's stream (event pairs around single launches add ~7 us of launch latency to a 20 us kernel)
     barrier()
-    n_k = min(args.steps, 4096)
+    n_k = min(max(args.steps, 256), 4096)       # at least 256 launches: a run of 20 would mostly time its own start
     k_ms = mppi.timeRollout(pose, n_k)
     k_n = n_k
     clocks = sampler.stop()
