@@ -265,19 +265,27 @@ __device__ __forceinline__ void mppi_sincos_small(const MppiArgs &a, double d, d
 }
 
 // ---- segmented warp scans over the G lanes of a rollout -----------------------------------------------------------
-// (Plain shuffles and selects.  A version that took shfl.sync's "source lane in range" predicate and predicated the
-// dependent fp64 arithmetic on it in inline PTX was built and measured: ptxas turns the predicated fp64 operations back
-// into FSEL pairs on the 32-bit halves and the unpack / repack around the asm costs a hundred register moves per pass.)
+// A lane outside a scan step (its partner would lie in another rollout's segment) keeps its value.  For the additive scans
+// that is x = fma(other, m, x) with m = 1.0 or 0.0 built by ONE select on the high word: written as `if (g >= d) x += other`
+// it compiles to DADD + two FSEL on the 32-bit halves + the moves that re-pair them (549 instructions per pass against 516).
+// (The masks in a shared-memory table gave 513 instructions and a SLOWER loop: their loads sit on the scans' dependent chain.
+// A version that took shfl.sync's "source lane in range" predicate and predicated the dependent fp64 arithmetic on it in
+// inline PTX was built and measured too: ptxas turns the predicated fp64 operations back into FSEL pairs and the unpack /
+// repack around the asm costs a hundred register moves per pass.)
+// 1.0 where the condition holds, else 0.0: a select on the high word (x = fma(other, m, x) then is the guarded addition in
+// one instruction, bit for bit: the product is exact and x + 0 = x)
+__device__ __forceinline__ double mppi_mask(bool on) { return __hiloint2double(on ? 0x3FF00000 : 0, 0); }
+
 template <int G>
 __device__ __forceinline__ void scan_rot_up(double &tc, double &ts, double &tth, int d, int g)
 {
   const double oc = __shfl_up_sync(kFullMask, tc, d, G), os = __shfl_up_sync(kFullMask, ts, d, G);
   const double ot = __shfl_up_sync(kFullMask, tth, d, G);
+  tth = fma(ot, mppi_mask(g >= d), tth);
   if (g >= d) {
     const double nc = fma(tc, oc, -(ts * os));
     ts = fma(tc, os, ts * oc);
     tc = nc;
-    tth += ot;
   }
 }
 
@@ -285,14 +293,15 @@ template <int G>
 __device__ __forceinline__ void scan_add2_up(double &x, double &y, int d, int g)
 {
   const double ox = __shfl_up_sync(kFullMask, x, d, G), oy = __shfl_up_sync(kFullMask, y, d, G);
-  if (g >= d) { x += ox; y += oy; }
+  const double m = mppi_mask(g >= d);
+  x = fma(ox, m, x); y = fma(oy, m, y);
 }
 
 template <int G>
 __device__ __forceinline__ void scan_add_down(double &x, int d, int g)
 {
   const double ox = __shfl_down_sync(kFullMask, x, d, G);
-  if (g + d < G) x += ox;
+  x = fma(ox, mppi_mask(g + d < G), x);
 }
 
 // value of the neighbouring lane inside the segment (delta 1), or `edge` at the segment boundary
